@@ -1,0 +1,364 @@
+// K4 — kNN / radius neighbour search (torch_cluster.knn_graph / radius_graph semantics as called
+// at utils/pointcloud_utils.py:10,12).  Tiled brute force: a CTA stages TILE candidate points in
+// shared memory; each warp owns QPW queries and evaluates 32 candidates per step (one per lane)
+// against all of them; survivors of the "better than the current k-th" test are inserted with
+// warp shuffles into a per-query candidate set spread across the lanes; a warp-shuffle bitonic
+// sort orders the final set.  Keys are (fp32 distance bits << 32 | index): one unsigned compare
+// gives "ascending distance, lower index wins ties".  Distances use individually rounded
+// mul/add in a fixed association so they are bit-identical to the oracle's.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace {
+using namespace dcb;
+
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_WARPS = KNN_THREADS / 32;
+constexpr int QPW = 4;
+constexpr int QPB = KNN_WARPS * QPW;  // queries per block
+constexpr int TILE = 1024;
+constexpr unsigned long long KEY_INF = ~0ull;
+
+__device__ __forceinline__ float sqdist(float qx, float qy, float qz, float px, float py, float pz) {
+  float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// largest g in [0, B) with ptr[g] <= q
+__device__ __forceinline__ int find_graph(const int64_t* __restrict__ ptr, int64_t B, int64_t q) {
+  int64_t lo = 0, hi = B - 1;
+  while (lo < hi) {
+    int64_t mid = (lo + hi + 1) >> 1;
+    if (ptr[mid] <= q) lo = mid; else hi = mid - 1;
+  }
+  return (int)lo;
+}
+
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
+  unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src);
+  unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+  return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long shfl_xor64(unsigned long long v, int m) {
+  unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
+  unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+template <int SLOTS>
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&k)[SLOTS], int lane) {
+  constexpr int n = 32 * SLOTS;
+#pragma unroll
+  for (int size = 2; size <= n; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+        const int ss = stride / 32;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          if ((s & ss) == 0) {
+            const bool asc = (((s * 32 + lane) & size) == 0);
+            unsigned long long a = k[s], b = k[s | ss];
+            if ((a > b) == asc) { k[s] = b; k[s | ss] = a; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          const bool asc = (((s * 32 + lane) & size) == 0);
+          unsigned long long o = shfl_xor64(k[s], stride);
+          const bool lower = (lane & stride) == 0;
+          const bool keepmin = (lower == asc);
+          k[s] = keepmin ? (k[s] < o ? k[s] : o) : (k[s] > o ? k[s] : o);
+        }
+      }
+    }
+  }
+}
+
+template <int SLOTS>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, int64_t B, int64_t N, int kk, int loop, int W,
+           int32_t* __restrict__ out) {
+  __shared__ float sx[TILE], sy[TILE], sz[TILE];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t qb0 = (int64_t)blockIdx.x * QPB;
+  const int64_t qb1 = min(N, qb0 + QPB) - 1;
+  const int64_t cand_lo = ptr[find_graph(ptr, B, qb0)];
+  const int64_t cand_hi = ptr[find_graph(ptr, B, qb1) + 1];
+
+  float qx[QPW], qy[QPW], qz[QPW];
+  int64_t lo[QPW], hi[QPW];
+  bool qv[QPW];
+  unsigned long long keys[QPW][SLOTS], thresh[QPW];
+  constexpr int CAP = 32 * SLOTS;
+#pragma unroll
+  for (int qi = 0; qi < QPW; ++qi) {
+    const int64_t q = qb0 + warp * QPW + qi;
+    qv[qi] = q < N;
+    const int64_t qq = qv[qi] ? q : (N - 1);
+    const int g = find_graph(ptr, B, qq);
+    lo[qi] = ptr[g];
+    hi[qi] = ptr[g + 1];
+    qx[qi] = pos[3 * qq]; qy[qi] = pos[3 * qq + 1]; qz[qi] = pos[3 * qq + 2];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) keys[qi][s] = (s * 32 + lane) < kk ? KEY_INF : 0ull;  // 0 = permanently unused slot
+    thresh[qi] = KEY_INF;
+  }
+
+  for (int64_t t0 = cand_lo; t0 < cand_hi; t0 += TILE) {
+    __syncthreads();
+    const int tile_n = (int)min((int64_t)TILE, cand_hi - t0);
+    for (int i = tid; i < tile_n; i += KNN_THREADS) {
+      const int64_t c = t0 + i;
+      sx[i] = pos[3 * c]; sy[i] = pos[3 * c + 1]; sz[i] = pos[3 * c + 2];
+    }
+    __syncthreads();
+    for (int j0 = 0; j0 < tile_n; j0 += 32) {
+      const int j = j0 + lane;
+      const bool inb = j < tile_n;
+      const float px = inb ? sx[j] : 0.f, py = inb ? sy[j] : 0.f, pz = inb ? sz[j] : 0.f;
+      const int64_t c = t0 + j;
+#pragma unroll
+      for (int qi = 0; qi < QPW; ++qi) {
+        const float d = sqdist(qx[qi], qy[qi], qz[qi], px, py, pz);
+        const bool ok = inb && qv[qi] && c >= lo[qi] && c < hi[qi];
+        const unsigned long long key = ok ? (((unsigned long long)__float_as_uint(d) << 32) | (unsigned)c) : KEY_INF;
+        unsigned m = __ballot_sync(0xffffffffu, key < thresh[qi]);
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const unsigned long long ck = shfl64(key, b);
+          if (ck < thresh[qi]) {
+            // locate the current maximum of the set, replace it, recompute the threshold
+            unsigned long long lmax = keys[qi][0];
+            int lslot = 0;
+#pragma unroll
+            for (int s = 1; s < SLOTS; ++s)
+              if (keys[qi][s] > lmax) { lmax = keys[qi][s]; lslot = s; }
+            unsigned long long wmax = lmax;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              unsigned long long t = shfl_xor64(wmax, o);
+              wmax = t > wmax ? t : wmax;
+            }
+            const int owner = __ffs(__ballot_sync(0xffffffffu, lmax == wmax)) - 1;
+            if (lane == owner) {
+#pragma unroll
+              for (int s = 0; s < SLOTS; ++s)
+                if (s == lslot) keys[qi][s] = ck;
+            }
+            // new maximum
+            lmax = keys[qi][0];
+#pragma unroll
+            for (int s = 1; s < SLOTS; ++s) lmax = keys[qi][s] > lmax ? keys[qi][s] : lmax;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              unsigned long long t = shfl_xor64(lmax, o);
+              lmax = t > lmax ? t : lmax;
+            }
+            thresh[qi] = lmax;
+          }
+        }
+      }
+    }
+  }
+
+  const int ndummy = CAP - kk;
+#pragma unroll
+  for (int qi = 0; qi < QPW; ++qi) {
+    const int64_t q = qb0 + warp * QPW + qi;
+    if (!qv[qi]) continue;  // warp-uniform
+    warp_bitonic_sort<SLOTS>(keys[qi], lane);
+    // rank of the self match among the real entries (or CAP if absent / loop)
+    int self_rank = CAP;
+    bool valid[SLOTS];
+    int idx[SLOTS], rank[SLOTS];
+    int nvalid = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      rank[s] = s * 32 + lane - ndummy;
+      valid[s] = rank[s] >= 0 && keys[qi][s] != KEY_INF;
+      idx[s] = (int)(unsigned)(keys[qi][s] & 0xffffffffull);
+      const bool is_self = valid[s] && !loop && (int64_t)idx[s] == q;
+      const unsigned sm = __ballot_sync(0xffffffffu, is_self);
+      if (sm) self_rank = s * 32 + (__ffs(sm) - 1) - ndummy;
+      nvalid += __popc(__ballot_sync(0xffffffffu, valid[s]));
+    }
+    const int nout = nvalid - (self_rank < CAP ? 1 : 0);
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      if (valid[s] && rank[s] != self_rank) {
+        const int p = rank[s] - (rank[s] > self_rank ? 1 : 0);
+        if (p < W) out[q * W + p] = idx[s];
+      }
+    }
+    for (int p = nout + lane; p < W; p += 32) out[q * W + p] = -1;
+  }
+}
+
+__global__ void __launch_bounds__(KNN_THREADS)
+radius_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, int64_t B, int64_t N, float r2, int cap,
+              int loop, int W, int32_t* __restrict__ out, int32_t* __restrict__ count_out) {
+  __shared__ float sx[TILE], sy[TILE], sz[TILE];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t qb0 = (int64_t)blockIdx.x * QPB;
+  const int64_t qb1 = min(N, qb0 + QPB) - 1;
+  const int64_t cand_lo = ptr[find_graph(ptr, B, qb0)];
+  const int64_t cand_hi = ptr[find_graph(ptr, B, qb1) + 1];
+  float qx[QPW], qy[QPW], qz[QPW];
+  int64_t lo[QPW], hi[QPW];
+  bool qv[QPW];
+  int cnt[QPW];
+#pragma unroll
+  for (int qi = 0; qi < QPW; ++qi) {
+    const int64_t q = qb0 + warp * QPW + qi;
+    qv[qi] = q < N;
+    const int64_t qq = qv[qi] ? q : (N - 1);
+    const int g = find_graph(ptr, B, qq);
+    lo[qi] = ptr[g]; hi[qi] = ptr[g + 1];
+    qx[qi] = pos[3 * qq]; qy[qi] = pos[3 * qq + 1]; qz[qi] = pos[3 * qq + 2];
+    cnt[qi] = 0;
+  }
+  for (int64_t t0 = cand_lo; t0 < cand_hi; t0 += TILE) {
+    __syncthreads();
+    const int tile_n = (int)min((int64_t)TILE, cand_hi - t0);
+    for (int i = tid; i < tile_n; i += KNN_THREADS) {
+      const int64_t c = t0 + i;
+      sx[i] = pos[3 * c]; sy[i] = pos[3 * c + 1]; sz[i] = pos[3 * c + 2];
+    }
+    __syncthreads();
+    bool all_full = true;
+#pragma unroll
+    for (int qi = 0; qi < QPW; ++qi) all_full = all_full && (!qv[qi] || cnt[qi] >= cap);
+    if (all_full) continue;  // still takes part in the tile loads above
+    for (int j0 = 0; j0 < tile_n; j0 += 32) {
+      const int j = j0 + lane;
+      const bool inb = j < tile_n;
+      const float px = inb ? sx[j] : 0.f, py = inb ? sy[j] : 0.f, pz = inb ? sz[j] : 0.f;
+      const int64_t c = t0 + j;
+#pragma unroll
+      for (int qi = 0; qi < QPW; ++qi) {
+        const float d = sqdist(qx[qi], qy[qi], qz[qi], px, py, pz);
+        const bool hit = inb && qv[qi] && c >= lo[qi] && c < hi[qi] && d < r2;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m && cnt[qi] < cap) {
+          const int p = cnt[qi] + __popc(m & ((1u << lane) - 1u));
+          if (hit && p < cap) out[(qb0 + warp * QPW + qi) * W + p] = (int32_t)c;
+          cnt[qi] = min(cap, cnt[qi] + __popc(m));
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // drop the self match (if it made it into the first `cap` hits), pad with -1
+#pragma unroll
+  for (int qi = 0; qi < QPW; ++qi) {
+    const int64_t q = qb0 + warp * QPW + qi;
+    if (!qv[qi]) continue;
+    int32_t* row = out + q * W;
+    const int n = cnt[qi];
+    int self_pos = n;
+    if (!loop) {
+      for (int p0 = 0; p0 < n; p0 += 32) {
+        const int p = p0 + lane;
+        const unsigned sm = __ballot_sync(0xffffffffu, p < n && (int64_t)row[p] == q);
+        if (sm) { self_pos = p0 + __ffs(sm) - 1; break; }
+      }
+    }
+    const int nout = n - (self_pos < n ? 1 : 0);
+    if (self_pos < n) {
+      for (int p0 = self_pos; p0 < n - 1; p0 += 32) {  // shift left by one, chunk by chunk in order
+        const int p = p0 + lane;
+        int32_t v = (p < n - 1) ? row[p + 1] : 0;
+        __syncwarp();
+        if (p < n - 1) row[p] = v;
+        __syncwarp();
+      }
+    }
+    for (int p = nout + lane; p < W; p += 32) row[p] = -1;
+    if (lane == 0 && count_out) count_out[q] = nout;
+  }
+}
+
+__global__ void nbr_count_kernel(const int32_t* __restrict__ nbr, int64_t N, int W, uint32_t* __restrict__ cnt) {
+  int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= N) return;
+  int c = 0;
+  for (int p = 0; p < W; ++p) c += nbr[q * W + p] >= 0;
+  cnt[q] = c;
+}
+
+__global__ void nbr_emit_kernel(const int32_t* __restrict__ nbr, int64_t N, int W, const uint32_t* __restrict__ off,
+                                int64_t* __restrict__ ei, int64_t cap, int64_t* __restrict__ num_out) {
+  int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= N) return;
+  int64_t o = off[q];
+  for (int p = 0; p < W; ++p) {
+    int v = nbr[q * W + p];
+    if (v >= 0) {
+      if (o < cap) { ei[o] = v; ei[cap + o] = q; }
+      ++o;
+    }
+  }
+  if (q == N - 1) *num_out = o;
+}
+}  // namespace
+
+extern "C" int dc_knn(const float* pos, const int64_t* ptr, int64_t B, int64_t N, int32_t k, int loop, int32_t* nbr_out,
+                      dc_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DC_REQUIRE(N >= 0 && B >= 1 && k >= 1, DC_EINVAL, "knn: bad sizes N=%lld B=%lld k=%d", (long long)N, (long long)B, k);
+  if (N == 0) return DC_OK;
+  DC_REQUIRE(pos && ptr && nbr_out, DC_EINVAL, "knn: null pointer");
+  const int kk = k + (loop ? 0 : 1);
+  DC_REQUIRE(kk <= 128, DC_ENOSUP, "knn: k=%d exceeds the supported maximum (127, or 128 with loop)", k);
+  const unsigned grid = (unsigned)cdiv(N, QPB);
+  if (kk <= 32) knn_kernel<1><<<grid, KNN_THREADS, 0, st>>>(pos, ptr, B, N, kk, loop, kk, nbr_out);
+  else if (kk <= 64) knn_kernel<2><<<grid, KNN_THREADS, 0, st>>>(pos, ptr, B, N, kk, loop, kk, nbr_out);
+  else knn_kernel<4><<<grid, KNN_THREADS, 0, st>>>(pos, ptr, B, N, kk, loop, kk, nbr_out);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+extern "C" int dc_radius(const float* pos, const int64_t* ptr, int64_t B, int64_t N, float r, int32_t max_nbr, int loop,
+                         int32_t* nbr_out, int32_t* count_out, dc_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DC_REQUIRE(N >= 0 && B >= 1 && max_nbr >= 1, DC_EINVAL, "radius: bad sizes");
+  if (N == 0) return DC_OK;
+  DC_REQUIRE(pos && ptr && nbr_out, DC_EINVAL, "radius: null pointer");
+  const int cap = max_nbr + (loop ? 0 : 1);
+  const float r2 = r * r;  // fp32 product, as torch_cluster
+  radius_kernel<<<(unsigned)cdiv(N, QPB), KNN_THREADS, 0, st>>>(pos, ptr, B, N, r2, cap, loop, cap, nbr_out, count_out);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+extern "C" size_t dc_nbr_to_edge_index_workspace_bytes(int64_t N) {
+  dcb::Carver c(nullptr);
+  c.take<uint32_t>(N > 0 ? N : 1);
+  c.take<uint32_t>(scan_num_blocks(N));
+  return c.used();
+}
+
+extern "C" int dc_nbr_to_edge_index(const int32_t* nbr, int64_t N, int32_t W, int64_t* edge_index, int64_t edge_cap,
+                                    int64_t* num_edges_out, void* workspace, size_t workspace_bytes, dc_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DC_REQUIRE(N >= 0 && W >= 0 && num_edges_out, DC_EINVAL, "nbr_to_edge_index: bad args");
+  if (N == 0 || W == 0) {
+    DC_CUDA(cudaMemsetAsync(num_edges_out, 0, sizeof(int64_t), st));
+    return DC_OK;
+  }
+  DC_REQUIRE(nbr && edge_index && workspace, DC_EINVAL, "nbr_to_edge_index: null pointer");
+  DC_REQUIRE(workspace_bytes >= dc_nbr_to_edge_index_workspace_bytes(N), DC_EWORKSPACE, "nbr_to_edge_index: workspace");
+  DC_REQUIRE((int64_t)N * W < (1ll << 32), DC_ENOSUP, "nbr_to_edge_index: N*W too large");
+  dcb::Carver c(workspace);
+  uint32_t* cnt = c.take<uint32_t>(N);
+  uint32_t* bsum = c.take<uint32_t>(scan_num_blocks(N));
+  nbr_count_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(nbr, N, W, cnt);
+  DC_LAUNCH_CHECK();
+  if (int rc = exclusive_scan_u32(cnt, N, bsum, st)) return rc;
+  nbr_emit_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(nbr, N, W, cnt, edge_index, edge_cap, num_edges_out);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}

@@ -1,0 +1,42 @@
+"""Edge construction and input features on the GPU (drop-ins for utils/graph_utils.py:7-20,
+utils/pointcloud_utils.py:7-13, utils/pos_encoding.py:6-44).  All arithmetic is in libdcb200."""
+import torch
+
+from . import ops
+from .data import Data
+
+
+def to_log_freq(x, N_freqs=3, dim=1):
+    """utils/pos_encoding.py:to_log_freq for the only configuration the reference uses
+    (``to_log_freq(pos, 3, 1)``, utils/graph_utils.py:16): [N,3] -> [N,21]."""
+    if N_freqs != 3 or x.dim() != 2 or x.shape[1] != 3 or dim not in (1, -1):
+        raise NotImplementedError("to_log_freq: only the reference configuration (N_freqs=3, [N,3], dim=1) is built")
+    return ops.posenc(x)
+
+
+def mesh_to_graph(vertices, triangles, encode=True, device="cuda"):
+    """utils/graph_utils.py:7-20 with (vertices, triangles) arrays in place of an Open3D mesh:
+    directed half-edges (a,b),(b,c),(c,a) per triangle, ``x = to_log_freq(pos)``."""
+    pos = torch.as_tensor(vertices).to(device=device, dtype=torch.float32)
+    tri = torch.as_tensor(triangles).to(device=device, dtype=torch.int64).reshape(-1, 3)
+    edge_index = ops.mesh_edges(tri)
+    x = ops.posenc(pos) if encode else pos
+    return Data(x=x, edge_index=edge_index, pos=pos)
+
+
+def knn_graph(x, k, batch=None, loop=False, ptr=None):
+    """torch_cluster.knn_graph(x, k, batch, loop, flow='source_to_target') -> int64 [2, E]."""
+    return ops.table_to_edge_index(ops.knn_table(x, k, batch=batch, ptr=ptr, loop=loop))
+
+
+def radius_graph(x, r, batch=None, loop=False, max_num_neighbors=32, ptr=None):
+    """torch_cluster.radius_graph(x, r, batch, loop, max_num_neighbors) -> int64 [2, E]."""
+    tab, _ = ops.radius_table(x, r, batch=batch, ptr=ptr, loop=loop, max_num_neighbors=max_num_neighbors)
+    return ops.table_to_edge_index(tab)
+
+
+def construct_graph(point_cloud, k=None, radius=None):
+    """utils/pointcloud_utils.py:7-13."""
+    if radius is not None:
+        return radius_graph(point_cloud, radius, batch=None, loop=False)
+    return knn_graph(point_cloud, k, batch=None, loop=False)

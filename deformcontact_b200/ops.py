@@ -1,0 +1,290 @@
+"""Tensor-level wrappers over the C ABI (``include/dcb200.h``) and the ``dcb200::`` torch ops.
+
+Every function takes CUDA tensors, allocates outputs / workspaces with the torch caching
+allocator, enqueues on torch's current stream and returns immediately (no host sync except
+where a data-dependent output size must be read back: ``knn_graph`` / ``radius_graph``).
+PyTorch is plumbing here: device memory and streams.  No eager fallback exists.
+"""
+import ctypes as C
+
+import torch
+
+from . import _abi
+from ._abi import GEMM_AUTO, GEMM_FP32, GEMM_TF32X3  # noqa: F401
+
+_i32, _i64, _f32 = torch.int32, torch.int64, torch.float32
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise _abi.DcError(f"{name}: expected a CUDA tensor (libdcb200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _abi.DcError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+
+
+def _rows(t, name):
+    """2-D tensor with unit inner stride -> (tensor, leading dimension)."""
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise _abi.DcError(f"{name}: expected a 2-D tensor with contiguous rows")
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------- K5
+def csr_build(edge_index, num_nodes, group_by=0, drop_self_loops=False):
+    """-> (rowptr int32 [N+1], nbr int32 [E], eid int32 [E]); see dc_csr_build."""
+    _need(edge_index, _i64, "edge_index")
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise _abi.DcError("edge_index must be int64 [2, E]")
+    ei = edge_index.contiguous()
+    E, dev = ei.shape[1], ei.device
+    rowptr = torch.empty(num_nodes + 1, dtype=_i32, device=dev)
+    nbr = torch.empty(E, dtype=_i32, device=dev)
+    eid = torch.empty(E, dtype=_i32, device=dev)
+    nb = _abi.lib().dc_csr_build_workspace_bytes(num_nodes, E)
+    ws = _workspace(nb, dev)
+    _abi.call("dc_csr_build", _ptr(ei), E, num_nodes, int(group_by), int(bool(drop_self_loops)), _ptr(rowptr), _ptr(nbr),
+              _ptr(eid), _ptr(ws), ws.numel(), _stream())
+    return rowptr, nbr, eid
+
+
+def deg_inv_sqrt(rowptr, num_nodes, add_self_loop=False):
+    dis = torch.empty(num_nodes, dtype=_f32, device=rowptr.device)
+    _abi.call("dc_deg_inv_sqrt", _ptr(rowptr), num_nodes, int(bool(add_self_loop)), _ptr(dis), _stream())
+    return dis
+
+
+class GraphCSR:
+    """Device-resident structure of one (batched) graph: CSR by target for the forward
+    aggregation, CSR by source for its transpose (built lazily, used by backward), and the
+    symmetric-normalisation vector ``dis = deg^-1/2``.
+
+    mode "tag": PyG ``gcn_norm(add_self_loops=False)`` (TAGConv) — loops kept as ordinary edges.
+    mode "gcn": ``add_remaining_self_loops`` — existing loops dropped, one appended per node.
+    mode "gat": ``remove_self_loops`` + ``add_self_loops`` — same structure as "gcn", no dis.
+    """
+
+    def __init__(self, edge_index, num_nodes, mode="tag"):
+        if mode not in ("tag", "gcn", "gat", "plain"):
+            raise ValueError(mode)
+        self.mode, self.N, self.E = mode, int(num_nodes), int(edge_index.shape[1])
+        self.edge_index = edge_index
+        self.self_loops = mode in ("gcn", "gat")
+        self.rowptr, self.nbr, self.eid = csr_build(edge_index, self.N, 0, self.self_loops)
+        self.dis = deg_inv_sqrt(self.rowptr, self.N, mode == "gcn") if mode in ("tag", "gcn") else None
+        self._t = None
+
+    @property
+    def t(self):
+        """(rowptr, nbr, eid) grouped by source — the transposed structure."""
+        if self._t is None:
+            self._t = csr_build(self.edge_index, self.N, 1, self.self_loops)
+        return self._t
+
+
+_CSR_CACHE = {}
+_CSR_CACHE_MAX = 16
+
+
+def graph_csr(edge_index, num_nodes, mode="tag"):
+    """Structure cache: ``conv(x, edge_index)`` (models/model.py:71,77) passes the same
+    ``edge_index`` tensor to every layer and hop, so the CSR pair is built once per batch.
+    Keyed on storage identity + version; the entry pins the tensor so the address cannot be
+    recycled while cached."""
+    if isinstance(edge_index, GraphCSR):
+        return edge_index
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), mode,
+           edge_index.device.index)
+    hit = _CSR_CACHE.get(key)
+    if hit is not None:
+        return hit
+    g = GraphCSR(edge_index, num_nodes, mode)
+    if len(_CSR_CACHE) >= _CSR_CACHE_MAX:
+        _CSR_CACHE.pop(next(iter(_CSR_CACHE)))
+    _CSR_CACHE[key] = g
+    return g
+
+
+def clear_csr_cache():
+    _CSR_CACHE.clear()
+
+
+# ----------------------------------------------------------------------------- K1
+def spmm(rowptr, nbr, h, dis=None, edge_w=None, edge_w_index=None, self_w=None, add=None, self_loop=False, bias=None,
+         relu=False, out=None):
+    """out[i] = act(add[i] + sum_e w_e h[nbr[e]] (+ self term) + bias); see dc_spmm."""
+    _need(h, _f32, "h")
+    ldh = _rows(h, "h")
+    N, F = h.shape
+    if out is None:
+        out = torch.empty((N, F), dtype=_f32, device=h.device)
+    ldo = _rows(out, "out")
+    ldadd = _rows(add, "add") if add is not None else 0
+    for t, n in ((dis, "dis"), (edge_w, "edge_w"), (self_w, "self_w"), (add, "add"), (bias, "bias")):
+        _need(t, _f32, n)
+    _abi.call("dc_spmm", _ptr(rowptr), _ptr(nbr), _ptr(dis), _ptr(edge_w), _ptr(edge_w_index), _ptr(self_w), _ptr(h), ldh,
+              _ptr(out), ldo, _ptr(add), ldadd, N, F, int(bool(self_loop)), _ptr(bias), int(bool(relu)), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- K2 / K3
+def gemm(segs, M, N, trans_a=False, trans_b=True, bias=None, relu=False, out=None, accumulate=False,
+         precision=GEMM_AUTO):
+    """C[M,N] = act(sum_s opA(A_s) opB(B_s) + bias) (+C); segs = [(A_s, B_s), ...]; see dc_gemm."""
+    arr = (_abi.GemmSeg * len(segs))()
+    ktot = 0
+    dev = segs[0][0].device
+    for i, (A, B) in enumerate(segs):
+        _need(A, _f32, "A"), _need(B, _f32, "B")
+        lda, ldb = _rows(A, "A"), _rows(B, "B")
+        K = A.shape[0] if trans_a else A.shape[1]
+        Kb = B.shape[1] if trans_b else B.shape[0]
+        Ma = A.shape[1] if trans_a else A.shape[0]
+        Nb = B.shape[0] if trans_b else B.shape[1]
+        if K != Kb or Ma != M or Nb != N:
+            raise _abi.DcError(f"gemm: segment {i} shapes {tuple(A.shape)} x {tuple(B.shape)} do not give [{M},{N}]")
+        arr[i] = _abi.GemmSeg(A.data_ptr(), lda, B.data_ptr(), ldb, K)
+        ktot += K
+    if out is None:
+        out = torch.empty((M, N), dtype=_f32, device=dev)
+    ldc = _rows(out, "out")
+    nb = _abi.lib().dc_gemm_workspace_bytes(M, N, ktot, int(trans_a), int(trans_b))
+    ws = _workspace(nb, dev) if nb else None
+    _abi.call("dc_gemm", arr, len(segs), int(trans_a), int(trans_b), M, N, _ptr(out), ldc, _ptr(bias), int(bool(relu)),
+              int(bool(accumulate)), int(precision), _ptr(ws), nb, _stream())
+    return out
+
+
+def colsum(X):
+    _need(X, _f32, "X")
+    ldx = _rows(X, "X")
+    M, N = X.shape
+    out = torch.empty(N, dtype=_f32, device=X.device)
+    nb = _abi.lib().dc_colsum_workspace_bytes(M, N)
+    ws = _workspace(nb, X.device)
+    _abi.call("dc_colsum", _ptr(X), ldx, M, N, _ptr(out), _ptr(ws), nb, _stream())
+    return out
+
+
+def relu_bwd(Y, dY):
+    Y, dY = Y.contiguous(), dY.contiguous()
+    dX = torch.empty_like(dY)
+    _abi.call("dc_relu_bwd", _ptr(Y), _ptr(dY), _ptr(dX), Y.numel(), _stream())
+    return dX
+
+
+# ----------------------------------------------------------------------------- K4
+def _ptr_tensor(num_points, batch, ptr, device):
+    if ptr is not None:
+        return ptr.to(device=device, dtype=_i64).contiguous()
+    if batch is None:
+        return torch.tensor([0, num_points], dtype=_i64, device=device)
+    counts = torch.bincount(batch.to(device))
+    return torch.cat([counts.new_zeros(1), counts.cumsum(0)]).to(_i64)
+
+
+def knn_table(pos, k, batch=None, ptr=None, loop=False):
+    """int32 [N, k (+1 if not loop)] neighbour table, ascending (distance, index), -1 padded."""
+    _need(pos, _f32, "pos")
+    pos = pos.contiguous()
+    N = pos.shape[0]
+    p = _ptr_tensor(N, batch, ptr, pos.device)
+    W = k + (0 if loop else 1)
+    tab = torch.empty((N, W), dtype=_i32, device=pos.device)
+    _abi.call("dc_knn", _ptr(pos), _ptr(p), p.numel() - 1, N, k, int(bool(loop)), _ptr(tab), _stream())
+    return tab
+
+
+def radius_table(pos, r, batch=None, ptr=None, loop=False, max_num_neighbors=32):
+    _need(pos, _f32, "pos")
+    pos = pos.contiguous()
+    N = pos.shape[0]
+    p = _ptr_tensor(N, batch, ptr, pos.device)
+    W = max_num_neighbors + (0 if loop else 1)
+    tab = torch.empty((N, W), dtype=_i32, device=pos.device)
+    cnt = torch.empty(N, dtype=_i32, device=pos.device)
+    _abi.call("dc_radius", _ptr(pos), _ptr(p), p.numel() - 1, N, float(r), max_num_neighbors, int(bool(loop)), _ptr(tab),
+              _ptr(cnt), _stream())
+    return tab, cnt
+
+
+def table_to_edge_index(tab):
+    """Padded neighbour table -> int64 [2, E] (row 0 = neighbour, row 1 = query).  Reads E back
+    (one host sync) because the output shape is data dependent, like torch_cluster."""
+    N, W = tab.shape
+    cap = N * W
+    ei = torch.empty((2, max(cap, 1)), dtype=_i64, device=tab.device)
+    num = torch.zeros(1, dtype=_i64, device=tab.device)
+    nb = _abi.lib().dc_nbr_to_edge_index_workspace_bytes(N)
+    ws = _workspace(nb, tab.device)
+    _abi.call("dc_nbr_to_edge_index", _ptr(tab), N, W, _ptr(ei), max(cap, 1), _ptr(num), _ptr(ws), nb, _stream())
+    E = int(num.item())
+    return ei[:, :E].contiguous() if E != cap else ei
+
+
+# ----------------------------------------------------------------------------- A6
+def mesh_edges(triangles, offset=0, out=None, start=0):
+    _need(triangles, _i64, "triangles")
+    tri = triangles.contiguous()
+    T = tri.shape[0]
+    if out is None:
+        out = torch.empty((2, 3 * T), dtype=_i64, device=tri.device)
+    _abi.call("dc_mesh_edges", _ptr(tri), T, int(offset), _ptr(out), out.shape[1], int(start), _stream())
+    return out
+
+
+def posenc(pos, out=None, col0=0):
+    _need(pos, _f32, "pos")
+    pos = pos.contiguous()
+    N = pos.shape[0]
+    if out is None:
+        out = torch.empty((N, 21), dtype=_f32, device=pos.device)
+    _abi.call("dc_posenc", _ptr(pos), N, _ptr(out), _rows(out, "out"), int(col0), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- K6
+def gat_scores(xs, att_src, att_dst, heads, C_):
+    N = xs.shape[0]
+    a_src = torch.empty((N, heads), dtype=_f32, device=xs.device)
+    a_dst = torch.empty((N, heads), dtype=_f32, device=xs.device)
+    _abi.call("dc_gat_scores", _ptr(xs), _rows(xs, "xs"), N, heads, C_, _ptr(att_src.contiguous()), _ptr(att_dst.contiguous()),
+              _ptr(a_src), _ptr(a_dst), _stream())
+    return a_src, a_dst
+
+
+def gat_softmax(g, a_src, a_dst, slope):
+    alpha_e = torch.zeros(max(g.E, 1), dtype=_f32, device=a_src.device)
+    alpha_s = torch.empty(g.N, dtype=_f32, device=a_src.device)
+    _abi.call("dc_gat_softmax", _ptr(g.rowptr), _ptr(g.nbr), _ptr(g.eid), _ptr(a_src), _ptr(a_dst), float(slope), g.N,
+              _ptr(alpha_e), _ptr(alpha_s), _stream())
+    return alpha_e, alpha_s
+
+
+def gat_bwd_edge(g, a_src, a_dst, slope, alpha_e, alpha_s, xs, dout):
+    dz_e = torch.zeros(max(g.E, 1), dtype=_f32, device=xs.device)
+    dz_s = torch.empty(g.N, dtype=_f32, device=xs.device)
+    da_dst = torch.empty(g.N, dtype=_f32, device=xs.device)
+    _abi.call("dc_gat_bwd_edge", _ptr(g.rowptr), _ptr(g.nbr), _ptr(g.eid), _ptr(a_src), _ptr(a_dst), float(slope),
+              _ptr(alpha_e), _ptr(alpha_s), _ptr(xs), _rows(xs, "xs"), _ptr(dout), _rows(dout, "dout"), xs.shape[1], g.N,
+              _ptr(dz_e), _ptr(dz_s), _ptr(da_dst), _stream())
+    return dz_e, dz_s, da_dst
+
+
+def segment_sum(rowptr, eid, val, init, N):
+    out = torch.empty(N, dtype=_f32, device=val.device)
+    _abi.call("dc_segment_sum", _ptr(rowptr), _ptr(eid), _ptr(val), _ptr(init), N, _ptr(out), _stream())
+    return out

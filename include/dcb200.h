@@ -1,0 +1,175 @@
+/* dcb200.h — C ABI of libdcb200.so: the sm_100a message-passing hot path of DeformContact.
+ *
+ * The reference (mahdi-slh/DeformContact) is pure Python and has no FFI of its own; the seam
+ * this library plugs into is the PyG layer call ``conv(x, edge_index)`` at
+ * models/model.py:71,77 and the edge builders at utils/graph_utils.py:7 /
+ * utils/pointcloud_utils.py:7.  Every entry point below names the reference (or pinned
+ * third-party) operation it replaces.  The Python binding is deformcontact_b200/_abi.py
+ * (ctypes); INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Contract (all entry points):
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated;
+ *  - the caller owns all memory (inputs, outputs, workspace); nothing is allocated, freed or
+ *    retained past return;
+ *  - all work is enqueued on `stream` (a cudaStream_t); no host synchronisation, no
+ *    default-stream use, no global mutable state  => re-entrant and CUDA-graph capturable;
+ *  - returns DC_OK (0) or a negative dc_status; dc_last_error() gives a thread-local message;
+ *  - features / weights are fp32, indices int32 inside the ABI (int64 edge_index is converted
+ *    by dc_csr_build); leading dimensions (ld*) are in elements;
+ *  - reductions are deterministic: per-receiver sums run in CSR order (= original edge order,
+ *    the sort is stable), split reductions use a fixed tree. No floating-point atomics.
+ */
+#ifndef DCB200_H
+#define DCB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DC_API __attribute__((visibility("default")))
+#else
+#define DC_API
+#endif
+
+typedef void* dc_stream_t; /* cudaStream_t */
+
+typedef enum {
+  DC_OK = 0,
+  DC_EINVAL = -1,     /* bad shape / alignment / null pointer */
+  DC_ENOSUP = -2,     /* unsupported width or mode */
+  DC_ECUDA = -3,      /* a CUDA runtime call failed; see dc_last_error() */
+  DC_EWORKSPACE = -4  /* workspace too small */
+} dc_status;
+
+DC_API int dc_version(void);
+DC_API const char* dc_last_error(void);
+
+/* ---------------------------------------------------------------- K5: CSR construction
+ * Replaces the per-forward ``gcn_norm`` + scatter index handling of PyG
+ * (nn/conv/gcn_conv.py:gcn_norm, called by TAGConv/GCNConv at models/model.py:71,77) and the
+ * int64 -> int32 conversion.  Stable LSD radix sort of the edges by `group_by` endpoint.
+ *   edge_index : int64 [2, E] row-major (row 0 = source j, row 1 = target i)
+ *   group_by   : 0 = by target (forward aggregation), 1 = by source (transpose, backward)
+ *   drop_self_loops : 1 removes edges with source == target (GCN/GAT "remaining self loops")
+ *   rowptr [N+1], nbr [E] (the other endpoint), eid [E] (original edge id; entries at and
+ *   beyond rowptr[N] are unspecified when self loops were dropped).
+ */
+DC_API size_t dc_csr_build_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+DC_API int dc_csr_build(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, int group_by,
+                 int drop_self_loops, int32_t* rowptr, int32_t* nbr, int32_t* eid, void* workspace,
+                 size_t workspace_bytes, dc_stream_t stream);
+
+/* dis[i] = (deg_i + add_self_loop)^-1/2 computed as 1/sqrt (two correctly rounded ops, like
+ * ATen's CPU pow(-0.5)); 0 when the degree is 0.  deg_i = rowptr[i+1] - rowptr[i] of the
+ * by-target CSR.  Replaces gcn_norm's deg/pow/masked_fill. */
+DC_API int dc_deg_inv_sqrt(const int32_t* rowptr_by_target, int64_t num_nodes, int add_self_loop, float* dis,
+                    dc_stream_t stream);
+
+/* ---------------------------------------------------------------- K1: gather / segmented sum
+ * Replaces MessagePassing.propagate(aggr='add') with message = w_e * x_j
+ * (PyG message_passing.py / tag_conv.py / gcn_conv.py; reference call sites models/model.py:71,77):
+ *   out[i, :] = add[i, :] + sum_{e in rowptr[i]..rowptr[i+1]} w_e * h[nbr[e], :]  (+ self-loop term)
+ *   w_e = (dis ? dis[nbr[e]] * dis[i] : 1) * (edge_w ? edge_w[edge_w_index ? edge_w_index[e] : e] : 1)
+ *   self_loop = 1 appends the term dis[i]*dis[i]*h[i] (or edge_w_self[i]*h[i]) after the edges.
+ * One warp (or sub-warp) per receiver, 128-bit row loads when F % 4 == 0 and rows are 16-B
+ * aligned, sequential fp32 mul+add in CSR order (bit-reproducible, no atomics).
+ * Epilogue: + bias[F] (row broadcast), then max(0, .) when relu = 1 (GCN/GAT `out + bias`).
+ * `add`, `dis`, `edge_w`, `edge_w_index`, `self_w`, `bias` may be NULL.  out may not alias h.
+ */
+DC_API int dc_spmm(const int32_t* rowptr, const int32_t* nbr, const float* dis, const float* edge_w,
+            const int32_t* edge_w_index, const float* self_w, const float* h, int64_t ldh, float* out, int64_t ldo, const float* add,
+            int64_t ldadd, int64_t num_nodes, int32_t F, int self_loop, const float* bias, int relu,
+            dc_stream_t stream);
+
+/* ---------------------------------------------------------------- K2/K3: layer GEMMs
+ * Replaces the Linear calls inside the PyG convs (nn/dense/linear.py; A3c in SURVEY.md).
+ * C[M,N] = act( sum_{s<nseg} opA(A_s)[M,K_s] * opB(B_s)[K_s,N] + bias[N] )  (+ C if accumulate)
+ *   transA = 0 : A_s stored [M, K_s] row-major (lda_s);  1 : stored [K_s, M] row-major
+ *   transB = 0 : B_s stored [K_s, N] row-major (ldb_s);  1 : stored [N, K_s] row-major
+ *   relu = 1 applies max(0, .) in the epilogue; bias may be NULL.
+ * precision: DC_GEMM_FP32 = fp32 FFMA (SIMT); DC_GEMM_TF32X3 = tcgen05 kind::tf32 with 3-term
+ * error-compensated split (fp32-class accuracy), only for transA=0, transB=1 shapes the tensor
+ * path supports (otherwise DC_ENOSUP); DC_GEMM_AUTO picks.
+ * Split-K (reduction over very long K, e.g. weight gradients over all nodes) uses `workspace`
+ * with a fixed-order second-stage sum.
+ */
+enum { DC_GEMM_AUTO = 0, DC_GEMM_FP32 = 1, DC_GEMM_TF32X3 = 2 };
+typedef struct {
+  const float* A;
+  int64_t lda;
+  const float* B;
+  int64_t ldb;
+  int64_t K;
+} dc_gemm_seg;
+DC_API size_t dc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K_total, int transA, int transB);
+DC_API int dc_gemm(const dc_gemm_seg* segs /*host array*/, int nseg, int transA, int transB, int64_t M, int64_t N,
+            float* C, int64_t ldc, const float* bias, int relu, int accumulate, int precision, void* workspace,
+            size_t workspace_bytes, dc_stream_t stream);
+
+/* colsum[n] = sum_m X[m, n] (bias gradient), deterministic two-stage tree. */
+DC_API size_t dc_colsum_workspace_bytes(int64_t M, int64_t N);
+DC_API int dc_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* workspace,
+              size_t workspace_bytes, dc_stream_t stream);
+
+/* dX = dY * (Y > 0)  (backward of the ReLU fused into dc_gemm's epilogue; models/model.py:71,77) */
+DC_API int dc_relu_bwd(const float* Y, const float* dY, float* dX, int64_t numel, dc_stream_t stream);
+
+/* ---------------------------------------------------------------- K4: kNN / radius graph
+ * Replaces torch_cluster.knn_graph / radius_graph as called at utils/pointcloud_utils.py:10,12
+ * (loop=False, flow source_to_target).  Brute force, tiled through shared memory, per-query
+ * warp-shuffle top-k.  Distances fp32 ((dx*dx)+(dy*dy))+(dz*dz) with no FMA contraction;
+ * ties -> lower index.  `ptr` (int64 [B+1], device) delimits independent point clouds
+ * (Batch.ptr); pass B = 1 and ptr = {0, N} for batch=None.
+ *  knn : nbr_out int32 [N, k] ascending (distance, index); -1 where fewer than k exist.
+ *        With loop=0 the search is for k+1 and the self match is removed (torch_cluster rule).
+ *  radius: up to max_nbr neighbours with d2 < r*r in ascending index order, self excluded
+ *        per torch_cluster's "search max_nbr+1 including self, then drop self" rule;
+ *        nbr_out int32 [N, max_nbr] padded with -1, count_out int32 [N].
+ */
+DC_API int dc_knn(const float* pos /*[N,3]*/, const int64_t* ptr, int64_t num_graphs, int64_t num_points, int32_t k,
+           int loop, int32_t* nbr_out, dc_stream_t stream);
+DC_API int dc_radius(const float* pos, const int64_t* ptr, int64_t num_graphs, int64_t num_points, float r,
+              int32_t max_nbr, int loop, int32_t* nbr_out, int32_t* count_out, dc_stream_t stream);
+/* Compacts a padded neighbour table into edge_index int64 [2, E_cap] (row 0 = neighbour,
+ * row 1 = query), queries ascending; *num_edges_out (device int64) receives E. */
+DC_API size_t dc_nbr_to_edge_index_workspace_bytes(int64_t num_points);
+DC_API int dc_nbr_to_edge_index(const int32_t* nbr, int64_t num_points, int32_t width, int64_t* edge_index,
+                         int64_t edge_cap, int64_t* num_edges_out, void* workspace, size_t workspace_bytes,
+                         dc_stream_t stream);
+
+/* ---------------------------------------------------------------- A6: mesh -> edges, features
+ * mesh_to_graph (utils/graph_utils.py:12-13): triangles int64 [T,3] -> edge_index int64 [2,3T]
+ * in per-triangle order (a,b),(b,c),(c,a); `offset` is added to every index (batching). */
+DC_API int dc_mesh_edges(const int64_t* triangles, int64_t num_tri, int64_t offset, int64_t* edge_index,
+                  int64_t edge_stride, int64_t edge_start, dc_stream_t stream);
+/* to_log_freq(pos, 3, 1) (utils/pos_encoding.py:6-44): [N,3] -> [N,21] at out[:, col0:col0+21]. */
+DC_API int dc_posenc(const float* pos, int64_t num_points, float* out, int64_t ldo, int32_t col0, dc_stream_t stream);
+
+/* ---------------------------------------------------------------- K6: GAT attention pieces
+ * (PyG nn/conv/gat_conv.py, utils/softmax.py)  a_src[n,h] = sum_c xs[n,h,c]*att_src[h,c] etc. */
+DC_API int dc_gat_scores(const float* xs, int64_t ld, int64_t num_nodes, int32_t heads, int32_t C, const float* att_src,
+                  const float* att_dst, float* a_src, float* a_dst, dc_stream_t stream);
+/* Per receiver i over its CSR edges plus the appended self loop:
+ *   e = leaky_relu(a_src[nbr] + a_dst[i], slope); alpha = exp(e - max) / (sum + 1e-16).
+ * Writes alpha_edge [E] indexed by ORIGINAL edge id (eid[p]) and alpha_self [N]; heads == 1 only. */
+DC_API int dc_gat_softmax(const int32_t* rowptr, const int32_t* nbr, const int32_t* eid, const float* a_src,
+                   const float* a_dst, float slope, int64_t num_nodes, float* alpha_edge, float* alpha_self,
+                   dc_stream_t stream);
+/* Backward of the attention scalars (one warp per receiver): dalpha_e = <dout[i], xs[nbr]>,
+ * softmax and leaky-relu backward; writes dz_edge [E] (by original edge id), dz_self [N] and
+ * da_dst[i] = sum of dz over i's edges and self loop. */
+DC_API int dc_gat_bwd_edge(const int32_t* rowptr, const int32_t* nbr, const int32_t* eid, const float* a_src,
+                    const float* a_dst, float slope, const float* alpha_edge, const float* alpha_self,
+                    const float* xs, int64_t ldx, const float* dout, int64_t ldd, int32_t C, int64_t num_nodes,
+                    float* dz_edge, float* dz_self, float* da_dst, dc_stream_t stream);
+/* out[i] = (init ? init[i] : 0) + sum_{p in row i} val[eid[p]]  (CSR order; e.g. da_src over the by-source CSR) */
+DC_API int dc_segment_sum(const int32_t* rowptr, const int32_t* eid, const float* val, const float* init,
+                   int64_t num_nodes, float* out, dc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCB200_H */

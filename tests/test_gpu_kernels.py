@@ -1,0 +1,219 @@
+"""GPU parity tests for the individual kernels (through the C ABI) against the CPU oracle."""
+import pytest
+import torch
+
+import oracle
+from oracle import convs as oconvs
+from helpers import assert_close, canonical
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dc():
+    import deformcontact_b200 as d
+    assert torch.cuda.is_available()
+    return d
+
+
+def _rand_graph(n, e, seed, self_loops=True, dup=True):
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    if not self_loops:
+        ei = ei[:, ei[0] != ei[1]]
+    if dup and ei.shape[1] > 4:
+        ei = torch.cat([ei, ei[:, :3]], 1)
+    return ei
+
+
+def _ref_csr(ei, n, by, drop):
+    e = ei.shape[1]
+    key = ei[0] if by else ei[1]
+    other = ei[1] if by else ei[0]
+    eid = torch.arange(e)
+    if drop:
+        m = ei[0] != ei[1]
+        key, other, eid = key[m], other[m], eid[m]
+    order = torch.sort(key, stable=True).indices
+    rowptr = torch.zeros(n + 1, dtype=torch.long)
+    rowptr[1:] = torch.bincount(key, minlength=n).cumsum(0)
+    return rowptr, other[order], eid[order]
+
+
+@pytest.mark.parametrize("n,e", [(1, 0), (5, 0), (7, 20), (1000, 8000), (2049, 2048), (70001, 300017), (300, 100000)])
+@pytest.mark.parametrize("by", [0, 1])
+@pytest.mark.parametrize("drop", [False, True])
+def test_csr_build(dc, n, e, by, drop):
+    ei = _rand_graph(n, e, seed=n + e, dup=e > 0) if e else torch.zeros(2, 0, dtype=torch.long)
+    rp, nbr, eid = dc.ops.csr_build(ei.cuda(), n, by, drop)
+    rrp, rnbr, reid = _ref_csr(ei, n, by, drop)
+    assert torch.equal(rp.cpu().long(), rrp)
+    m = int(rrp[-1])
+    assert torch.equal(nbr.cpu().long()[:m], rnbr)
+    assert torch.equal(eid.cpu().long()[:m], reid)
+
+
+def test_csr_hub_and_isolated(dc):
+    # star graph: one receiver with 50k in-edges, many isolated nodes
+    n = 60000
+    src = torch.arange(1, 50001)
+    ei = torch.stack([src, torch.zeros_like(src)])
+    rp, nbr, eid = dc.ops.csr_build(ei.cuda(), n, 0, False)
+    assert int(rp[1]) == 50000 and int(rp[-1]) == 50000
+    assert torch.equal(nbr.cpu().long(), src)
+    dis = dc.ops.deg_inv_sqrt(rp, n).cpu()
+    assert dis[1] == 0 and torch.isfinite(dis).all()
+    assert dis[0] == (torch.tensor(50000.0).sqrt().reciprocal())
+
+
+@pytest.mark.parametrize("F", [1, 3, 21, 24, 25, 32, 64, 100, 128, 256, 512])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_spmm_vs_oracle_propagate(dc, F, transpose):
+    n, e = 3000, 24000
+    ei = _rand_graph(n, e, seed=F)
+    g = torch.Generator().manual_seed(F)
+    h = torch.randn(n, F, generator=g)
+    _, w = oconvs.gcn_norm(ei, n, False)
+    G = dc.ops.GraphCSR(ei.cuda(), n, "tag")
+    if not transpose:
+        ref = oconvs.propagate(h, ei, w, n)
+        out = dc.ops.spmm(G.rowptr, G.nbr, h.cuda(), dis=G.dis)
+    else:
+        ref = oconvs.propagate(h, ei.flip(0), w, n)  # A_hat^T h
+        rp, nb, _ = G.t
+        out = dc.ops.spmm(rp, nb, h.cuda(), dis=G.dis)
+    assert_close(out, ref, what=f"spmm F={F} T={transpose}")
+    # same summation order and rounding as the CPU reference => expected bit-exact
+    assert torch.equal(out.cpu(), ref), "spmm is expected to be bit-identical to the CPU scatter order"
+    out2 = dc.ops.spmm(G.rowptr if not transpose else G.t[0], G.nbr if not transpose else G.t[1], h.cuda(), dis=G.dis)
+    assert torch.equal(out, out2), "run-to-run determinism"
+
+
+def test_spmm_add_bias_relu_strided(dc):
+    n, e, F = 1500, 9000, 64
+    ei = _rand_graph(n, e, 5)
+    g = torch.Generator().manual_seed(1)
+    big = torch.randn(n, 3 * F, generator=g).cuda()
+    h = big[:, F:2 * F]
+    add = torch.randn(n, F, generator=g).cuda()
+    bias = torch.randn(F, generator=g).cuda()
+    G = dc.ops.GraphCSR(ei.cuda(), n, "tag")
+    out = torch.zeros(n, 2 * F).cuda()
+    dc.ops.spmm(G.rowptr, G.nbr, h, dis=G.dis, add=add, bias=bias, relu=True, out=out[:, F:])
+    _, w = oconvs.gcn_norm(ei, n, False)
+    ref = torch.relu(add.cpu() + oconvs.propagate(h.cpu(), ei, w, n) + bias.cpu())
+    assert_close(out[:, F:], ref, what="spmm add/bias/relu")
+    assert torch.count_nonzero(out[:, :F]) == 0
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(300, 256, 84, 0, 1), (1000, 256, 1024, 0, 1), (513, 21, 256, 0, 0),
+                                         (256, 21, 5000, 1, 0), (256, 256, 40000, 1, 0), (1, 1, 1, 0, 1),
+                                         (129, 130, 17, 1, 1), (2, 64, 3000, 1, 0)])
+def test_gemm_simt(dc, M, N, K, ta, tb):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn((K, M) if ta else (M, K), generator=g)
+    B = torch.randn((N, K) if tb else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = ((A.t() if ta else A).double() @ (B.t() if tb else B).double() + bias.double())
+    out = dc.ops.gemm([(A.cuda(), B.cuda())], M, N, bool(ta), bool(tb), bias=bias.cuda(), precision=dc.ops.GEMM_FP32)
+    assert_close(out, ref.float(), what="gemm")
+    out_r = dc.ops.gemm([(A.cuda(), B.cuda())], M, N, bool(ta), bool(tb), bias=bias.cuda(), relu=True,
+                        precision=dc.ops.GEMM_FP32)
+    assert_close(out_r, ref.clamp_min(0).float(), what="gemm relu")
+    out2 = dc.ops.gemm([(A.cuda(), B.cuda())], M, N, bool(ta), bool(tb), bias=bias.cuda(), precision=dc.ops.GEMM_FP32)
+    assert torch.equal(out, out2)
+
+
+def test_gemm_segments_and_accumulate(dc):
+    g = torch.Generator().manual_seed(0)
+    M, N = 700, 256
+    As = [torch.randn(M, k, generator=g) for k in (21, 21, 21, 21)]
+    Bs = [torch.randn(N, k, generator=g) for k in (21, 21, 21, 21)]
+    ref = sum(a.double() @ b.double().t() for a, b in zip(As, Bs))
+    out = dc.ops.gemm([(a.cuda(), b.cuda()) for a, b in zip(As, Bs)], M, N, False, True, precision=dc.ops.GEMM_FP32)
+    assert_close(out, ref.float(), what="4-seg gemm")
+    dc.ops.gemm([(As[0].cuda(), Bs[0].cuda())], M, N, False, True, out=out, accumulate=True, precision=dc.ops.GEMM_FP32)
+    assert_close(out, (ref + As[0].double() @ Bs[0].double().t()).float(), what="accumulate")
+
+
+def test_colsum_relu_bwd(dc):
+    g = torch.Generator().manual_seed(2)
+    X = torch.randn(10007, 257, generator=g)
+    assert_close(dc.ops.colsum(X.cuda()), X.double().sum(0).float(), what="colsum")
+    Y = torch.randn(1000, 33, generator=g)
+    dY = torch.randn(1000, 33, generator=g)
+    assert torch.equal(dc.ops.relu_bwd(Y.cuda(), dY.cuda()).cpu(), dY * (Y > 0))
+
+
+@pytest.mark.parametrize("n,k", [(1, 3), (3, 5), (50, 8), (1000, 8), (3000, 16), (2500, 40), (1200, 100)])
+def test_knn_bit_exact(dc, n, k):
+    g = torch.Generator().manual_seed(n * 31 + k)
+    pos = torch.rand(n, 3, generator=g) - 0.5
+    ref = oracle.knn_graph(pos, k)
+    out = dc.knn_graph(pos.cuda(), k)
+    assert out.dtype == torch.int64 and out.shape[0] == 2
+    assert torch.equal(canonical(out), canonical(ref))
+    # neighbour order inside a query is also ascending (distance, index) — compare un-sorted too
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_knn_ties_duplicates_and_batch(dc):
+    g = torch.Generator().manual_seed(3)
+    pos = (torch.randint(0, 4, (600, 3), generator=g).float()) * 0.25  # lattice: many exact ties and duplicates
+    batch = torch.arange(3).repeat_interleave(200)
+    for b in (None, batch):
+        ref = oracle.knn_graph(pos, 6, b)
+        out = dc.knn_graph(pos.cuda(), 6, None if b is None else b.cuda())
+        assert torch.equal(canonical(out), canonical(ref))
+    ref = oracle.knn_graph(pos, 6, batch, loop=True)
+    out = dc.knn_graph(pos.cuda(), 6, batch.cuda(), loop=True)
+    assert torch.equal(canonical(out), canonical(ref))
+
+
+def test_knn_ragged_batch(dc):
+    g = torch.Generator().manual_seed(4)
+    sizes = [1, 7, 300, 2, 33, 1500]
+    pos = torch.rand(sum(sizes), 3, generator=g)
+    batch = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    ref = oracle.knn_graph(pos, 8, batch)
+    out = dc.knn_graph(pos.cuda(), 8, batch.cuda())
+    assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("r,mx", [(0.05, 32), (0.15, 32), (0.3, 32), (0.2, 4), (0.5, 64)])
+def test_radius_bit_exact(dc, r, mx):
+    g = torch.Generator().manual_seed(int(r * 100) + mx)
+    pos = torch.rand(1500, 3, generator=g)
+    batch = torch.repeat_interleave(torch.arange(3), torch.tensor([400, 100, 1000]))
+    for b in (None, batch):
+        ref = oracle.radius_graph(pos, r, b, max_num_neighbors=mx)
+        out = dc.radius_graph(pos.cuda(), r, None if b is None else b.cuda(), max_num_neighbors=mx)
+        assert torch.equal(canonical(out), canonical(ref))
+        assert torch.equal(out.cpu(), ref)
+
+
+def test_construct_graph_reference_api(dc):
+    pos = torch.rand(500, 3, generator=torch.Generator().manual_seed(9))
+    assert torch.equal(dc.construct_graph(pos.cuda(), k=5).cpu(), oracle.construct_graph(pos, k=5))
+    assert torch.equal(dc.construct_graph(pos.cuda(), radius=0.15).cpu(), oracle.construct_graph(pos, radius=0.15))
+
+
+def test_mesh_to_graph_and_posenc(dc, golden_dir):
+    v, t = oracle.uv_sphere(0.05, 20, (0.1, -0.2, 0.3))
+    ref = oracle.mesh_to_graph(v, t)
+    out = dc.mesh_to_graph(v, t)
+    assert torch.equal(out.edge_index.cpu(), ref.edge_index)
+    assert torch.equal(out.pos.cpu(), ref.pos)
+    assert_close(out.x, ref.x, tol=2e-6, what="posenc")
+    gold = torch.load(f"{golden_dir}/posenc.pt")
+    assert_close(dc.to_log_freq(gold["pos"].cuda(), 3, 1), gold["out"], tol=2e-6, what="posenc vs reference golden")
+
+
+def test_abi_errors(dc):
+    from deformcontact_b200 import _abi
+    with pytest.raises(_abi.DcError):
+        dc.ops.csr_build(torch.zeros(2, 3, dtype=torch.long), 4)          # CPU tensor: no CPU path
+    with pytest.raises(_abi.DcError):
+        dc.ops.spmm(None, None, torch.zeros(4, 4).cuda())                 # null pointers -> DC_EINVAL
+    with pytest.raises(_abi.DcError):
+        dc.ops.knn_table(torch.zeros(10, 3).cuda(), 500)                  # k too large -> DC_ENOSUP

@@ -1,0 +1,150 @@
+"""GPU parity of the drop-in layers and of GraphNet (fwd + bwd) against the CPU oracle.
+
+Tolerance: 1e-5 relative (north_star), metric in tests/helpers.py."""
+import pytest
+import torch
+
+import oracle
+from oracle import synthetic
+from helpers import assert_close, assert_close_arbiter
+import copy
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dc():
+    import deformcontact_b200 as d
+    return d
+
+
+def _graphs():
+    rest, rigid, _ = synthetic.make_batch(3, 400, 8)
+    mesh, _, _ = synthetic.make_batch(2, 400, 8, kind="mesh")
+    g = torch.Generator().manual_seed(5)
+    n = 500
+    weird = torch.randint(0, n - 20, (2, 3000), generator=g)          # duplicates, self loops, isolated tail nodes
+    weird = torch.cat([weird, torch.arange(10).repeat(2, 1)], 1)      # explicit self loops
+    return {"knn": (rest.x, rest.edge_index), "sphere": (rigid.x, rigid.edge_index), "mesh": (mesh.x, mesh.edge_index),
+            "weird": (torch.randn(n, 21, generator=g), weird), "empty": (torch.randn(6, 21, generator=g), torch.zeros(2, 0, dtype=torch.long))}
+
+
+def _pair(dc, name, fin, fout, seed=0):
+    torch.manual_seed(seed)
+    ref = getattr(oracle, name)(fin, fout)
+    with torch.no_grad():
+        ref.bias.uniform_(-0.2, 0.2)
+    ours = getattr(dc, name)(fin, fout)
+    ours.load_state_dict(ref.state_dict())          # same key names / shapes as PyG
+    assert [k for k, _ in ours.named_parameters()] == [k for k, _ in ref.named_parameters()]
+    return ref, ours.cuda()
+
+
+@pytest.mark.parametrize("layer", ["TAGConv", "GCNConv", "GATConv"])
+@pytest.mark.parametrize("graph", ["knn", "sphere", "mesh", "weird", "empty"])
+@pytest.mark.parametrize("fout", [32, 256])
+def test_layer_forward_backward(dc, layer, graph, fout):
+    x, ei = _graphs()[graph]
+    fin = x.shape[1]
+    ref, ours = _pair(dc, layer, fin, fout)
+    xr = x.clone().requires_grad_(True)
+    xo = x.clone().cuda().requires_grad_(True)
+    out_r = ref(xr, ei)
+    out_o = ours(xo, ei.cuda())
+    # fp64 arbiter: the same oracle layer evaluated in double precision
+    ref64 = copy.deepcopy(ref).double()
+    x64 = x.double().requires_grad_(True)
+    out_64 = ref64(x64, ei)
+    assert_close_arbiter(out_o, out_r, out_64, what=f"{layer}/{graph} out")
+    gseed = torch.Generator().manual_seed(1)
+    go = torch.randn(out_r.shape, generator=gseed)
+    out_r.backward(go)
+    out_o.backward(go.cuda())
+    out_64.backward(go.double())
+    assert_close_arbiter(xo.grad, xr.grad, x64.grad, what=f"{layer}/{graph} dx")
+    for (k, pr), (_, po), (_, p64) in zip(ref.named_parameters(), ours.named_parameters(), ref64.named_parameters()):
+        assert_close_arbiter(po.grad, pr.grad, p64.grad, what=f"{layer}/{graph} d{k}")
+
+
+@pytest.mark.parametrize("layer", ["TAGConv", "GCNConv", "GATConv"])
+def test_layer_fused_relu_and_hidden_width(dc, layer):
+    x0, ei = _graphs()["knn"]
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(x0.shape[0], 256, generator=g)
+    ref, ours = _pair(dc, layer, 256, 256, seed=3)
+    xr = x.clone().requires_grad_(True)
+    xo = x.clone().cuda().requires_grad_(True)
+    out_r = torch.relu(ref(xr, ei))
+    out_o = ours(xo, ei.cuda(), relu=True)
+    assert_close(out_o, out_r, what="fused relu out")
+    out_r.square().sum().backward()
+    out_o.square().sum().backward()
+    assert_close(xo.grad, xr.grad, what="fused relu dx")
+    for (k, pr), (_, po) in zip(ref.named_parameters(), ours.named_parameters()):
+        assert_close(po.grad, pr.grad, what=f"fused relu d{k}")
+
+
+@pytest.mark.parametrize("layer", ["TAGConv", "GCNConv", "GATConv"])
+def test_layer_determinism(dc, layer):
+    x, ei = _graphs()["knn"]
+    _, ours = _pair(dc, layer, 21, 64)
+    outs, grads = [], []
+    for _ in range(2):
+        dc.ops.clear_csr_cache()
+        ours.zero_grad()
+        xo = x.clone().cuda().requires_grad_(True)
+        o = ours(xo, ei.cuda())
+        o.sum().backward()
+        outs.append(o.detach().clone())
+        grads.append([xo.grad.clone()] + [p.grad.clone() for p in ours.parameters()])
+    assert torch.equal(outs[0], outs[1])
+    for a, b in zip(grads[0], grads[1]):
+        assert torch.equal(a, b)
+
+
+def test_layers_golden(dc, golden_dir):
+    gold = torch.load(f"{golden_dir}/layers.pt")
+    x, ei = gold["x"], gold["edge_index"]
+    for name, rec in gold["layers"].items():
+        layer = getattr(dc, name)(21, 16)
+        layer.load_state_dict(rec["state_dict"])
+        layer = layer.cuda()
+        xo = x.clone().cuda().requires_grad_(True)
+        out = layer(xo, ei.cuda())
+        assert_close(out, rec["out"], what=f"golden {name} out")
+        out.square().sum().backward()
+        assert_close(xo.grad, rec["dx"], what=f"golden {name} dx")
+        for k, p in layer.named_parameters():
+            assert_close(p.grad, rec["grads"][k], what=f"golden {name} d{k}")
+
+
+@pytest.mark.parametrize("backbone", ["TAGConv", "GCNConv", "GATConv"])
+def test_graphnet_golden_reference_wiring(dc, golden_dir, backbone):
+    """Fixture produced by the REFERENCE's own models/model.py:GraphNet (make_golden.py)."""
+    gold = torch.load(f"{golden_dir}/graphnet_{backbone}.pt")
+    rest, rigid, _ = synthetic.make_batch(gold["n_graphs"], gold["n_nodes"], gold["k"])
+    model = dc.load_model(gold["kw"])
+    model.load_state_dict(gold["state_dict"])       # reference state-dict keys load unchanged
+    model = model.cuda().eval()
+    brest = dc.Batch.from_data_list([dc.Data(x=d.x, edge_index=d.edge_index, pos=d.pos) for d in (rest[0], rest[1])]).to("cuda")
+    brig = dc.Batch.from_data_list([dc.Data(x=d.x, edge_index=d.edge_index, pos=d.pos) for d in (rigid[0], rigid[1])]).to("cuda")
+    out = model(brest, brig)
+    assert_close(out.pos, gold["out_pos"], what=f"GraphNet[{backbone}] vs reference wiring")
+
+
+@pytest.mark.parametrize("attn_group", [None, 2])
+def test_graphnet_train_step_vs_oracle(dc, attn_group):
+    rest, rigid, deformed = synthetic.make_batch(4, 300, 8)
+    torch.manual_seed(0)
+    ref = oracle.load_model(attn_group=attn_group)
+    ours = dc.load_model(attn_group=attn_group)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.cuda()
+    loss_r, l1_r, lc_r = oracle.train_step_loss(ref, rest, rigid, deformed)
+    loss_r.backward()
+    cu = lambda b: dc.Batch.from_data_list([dc.Data(x=d.x, edge_index=d.edge_index, pos=d.pos) for d in [b[i] for i in range(4)]]).to("cuda")
+    loss_o, l1_o, lc_o = dc.train_step_loss(ours, cu(rest), cu(rigid), cu(deformed))
+    loss_o.backward()
+    assert_close(loss_o, loss_r, what="loss")
+    for (k, pr), (_, po) in zip(ref.named_parameters(), ours.named_parameters()):
+        assert_close(po.grad, pr.grad, tol=5e-5, what=f"d{k}")   # whole-model chain (fp32 cuBLAS attention/decoder in between)
