@@ -28,6 +28,7 @@ _p, _i64, _i32, _f32, _sz, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C
 PROTOTYPES = {
     "dc_version": (_int, []),
     "dc_last_error": (C.c_char_p, []),
+    "dc_launch_count": (C.c_uint64, []),
     "dc_csr_build_workspace_bytes": (_sz, [_i64, _i64]),
     "dc_csr_build": (_int, [_p, _i64, _i64, _int, _int, _p, _p, _p, _p, _sz, _p]),
     "dc_deg_inv_sqrt": (_int, [_p, _i64, _int, _p, _p]),

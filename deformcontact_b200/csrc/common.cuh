@@ -30,7 +30,14 @@ void set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
-#define DC_LAUNCH_CHECK() DC_CUDA(cudaPeekAtLastError())
+void count_launches(int n);
+// every kernel launch site is followed by DC_LAUNCHED(n) (n = launches since the last check)
+#define DC_LAUNCHED(n)                  \
+  do {                                  \
+    dcb::count_launches(n);             \
+    DC_CUDA(cudaPeekAtLastError());     \
+  } while (0)
+#define DC_LAUNCH_CHECK() DC_LAUNCHED(1)
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -166,13 +166,13 @@ extern "C" int dc_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int
     if (int rc = exclusive_scan_u32(counts, p.L, bsum, st)) return rc;
     rs_scatter_kernel<<<(unsigned)p.nblocks, RS_THREADS, 0, st>>>(k0, v0, k1, v1, E, shift, mask, p.nbins, counts,
                                                                  (int)p.nblocks);
-    DC_LAUNCH_CHECK();
+    DC_LAUNCHED(2);
     uint32_t* tk = k0; k0 = k1; k1 = tk;
     int32_t* tv = v0; v0 = v1; v1 = tv;
   }
   csr_rowptr_kernel<<<(unsigned)cdiv(N + 1, 256), 256, 0, st>>>(k0, E, N, rowptr);
   csr_edges_kernel<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(v0, edge_index, E, group_by, nbr, eid);
-  DC_LAUNCH_CHECK();
+  DC_LAUNCHED(2);
   return DC_OK;
 }
 

@@ -1,7 +1,9 @@
 #include <stdarg.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace dcb {
+unsigned long long launches();
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -9,7 +11,12 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
 }  // namespace dcb
 
 extern "C" int dc_version(void) { return 100; }
 extern "C" const char* dc_last_error(void) { return dcb::g_err; }
+
+extern "C" uint64_t dc_launch_count(void) { return dcb::launches(); }

@@ -198,7 +198,7 @@ extern "C" int dc_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, floa
   dim3 grid((unsigned)cdiv(N, 32), (unsigned)chunks);
   colsum_stage1<<<grid, 256, 0, st>>>(X, ldx, M, N, static_cast<float*>(workspace));
   colsum_stage2<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(static_cast<float*>(workspace), chunks, N, out);
-  DC_LAUNCH_CHECK();
+  DC_LAUNCHED(2);
   return DC_OK;
 }
 
@@ -249,7 +249,7 @@ extern "C" int dc_gat_softmax(const int32_t* rowptr, const int32_t* nbr, const i
                               dc_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (N <= 0) return DC_OK;
-  DC_REQUIRE(rowptr && nbr && eid && a_src && a_dst && alpha_edge && alpha_self, DC_EINVAL, "gat_softmax: null pointer");
+  DC_REQUIRE(rowptr && a_src && a_dst && alpha_edge && alpha_self, DC_EINVAL, "gat_softmax: null pointer");
   gat_softmax_kernel<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(rowptr, nbr, eid, a_src, a_dst, slope, N, alpha_edge, alpha_self);
   DC_LAUNCH_CHECK();
   return DC_OK;
@@ -261,7 +261,7 @@ extern "C" int dc_gat_bwd_edge(const int32_t* rowptr, const int32_t* nbr, const 
                                float* dz_edge, float* dz_self, float* da_dst, dc_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (N <= 0) return DC_OK;
-  DC_REQUIRE(rowptr && nbr && eid && a_src && a_dst && alpha_edge && alpha_self && xs && dout && dz_edge && dz_self && da_dst,
+  DC_REQUIRE(rowptr && a_src && a_dst && alpha_edge && alpha_self && xs && dout && dz_edge && dz_self && da_dst,
              DC_EINVAL, "gat_bwd_edge: null pointer");
   gat_bwd_edge_kernel<<<(unsigned)cdiv(N, 8), 256, 0, st>>>(rowptr, nbr, eid, a_src, a_dst, slope, alpha_edge, alpha_self,
                                                             xs, ldx, dout, ldd, C, N, dz_edge, dz_self, da_dst);
@@ -273,7 +273,7 @@ extern "C" int dc_segment_sum(const int32_t* rowptr, const int32_t* eid, const f
                               float* out, dc_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (N <= 0) return DC_OK;
-  DC_REQUIRE(rowptr && eid && val && out, DC_EINVAL, "segment_sum: null pointer");
+  DC_REQUIRE(rowptr && val && out, DC_EINVAL, "segment_sum: null pointer");
   segment_sum_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(rowptr, eid, val, init, N, out);
   DC_LAUNCH_CHECK();
   return DC_OK;

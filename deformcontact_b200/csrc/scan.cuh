@@ -94,7 +94,7 @@ static inline int exclusive_scan_u32(uint32_t* data, int64_t L, uint32_t* blocks
   scan_reduce_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(data, L, blocksum);
   scan_blocksums_kernel<<<1, SCAN_THREADS, 0, st>>>(blocksum, nb);
   scan_apply_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(data, L, blocksum);
-  DC_LAUNCH_CHECK();
+  DC_LAUNCHED(3);
   return DC_OK;
 }
 }  // namespace dcb

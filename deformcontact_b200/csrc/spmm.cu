@@ -156,7 +156,7 @@ extern "C" int dc_spmm(const int32_t* rowptr, const int32_t* nbr, const float* d
   cudaStream_t st = (cudaStream_t)stream_;
   DC_REQUIRE(N >= 0 && F >= 0, DC_EINVAL, "spmm: negative size");
   if (N == 0 || F == 0) return DC_OK;
-  DC_REQUIRE(rowptr && nbr && h && out, DC_EINVAL, "spmm: null pointer");
+  DC_REQUIRE(rowptr && h && out, DC_EINVAL, "spmm: null pointer");  // nbr may be NULL for an edgeless graph
   DC_REQUIRE(ldh >= F && ldo >= F && (!add || ldadd >= F), DC_EINVAL, "spmm: leading dimension < F");
   DC_REQUIRE(h != out, DC_EINVAL, "spmm: out must not alias h");
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };

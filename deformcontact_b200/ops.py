@@ -14,6 +14,26 @@ from ._abi import GEMM_AUTO, GEMM_FP32, GEMM_TF32X3  # noqa: F401
 
 _i32, _i64, _f32 = torch.int32, torch.int64, torch.float32
 
+# Optional live profiling (bench.py): when set to a list, every spmm / gemm call is bracketed by
+# CUDA events on the launching stream and a record with its algorithmic bytes / flops is appended.
+PROFILER = None
+
+
+def _prof_begin():
+    if PROFILER is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _prof_end(e0, **rec):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    PROFILER.append(dict(e0=e0, e1=e1, **rec))
+
 
 def _ptr(t):
     return None if t is None else t.data_ptr()
@@ -135,8 +155,13 @@ def spmm(rowptr, nbr, h, dis=None, edge_w=None, edge_w_index=None, self_w=None, 
     ldadd = _rows(add, "add") if add is not None else 0
     for t, n in ((dis, "dis"), (edge_w, "edge_w"), (self_w, "self_w"), (add, "add"), (bias, "bias")):
         _need(t, _f32, n)
+    e0 = _prof_begin()
     _abi.call("dc_spmm", _ptr(rowptr), _ptr(nbr), _ptr(dis), _ptr(edge_w), _ptr(edge_w_index), _ptr(self_w), _ptr(h), ldh,
               _ptr(out), ldo, _ptr(add), ldadd, N, F, int(bool(self_loop)), _ptr(bias), int(bool(relu)), _stream())
+    if e0 is not None:
+        E = nbr.numel()
+        _prof_end(e0, op="spmm", F=F, N=N, E=E,
+                  bytes=8 * N * F + 4 * E + 8 * N + 4 + (4 * N * F if add is not None else 0))
     return out
 
 
@@ -163,8 +188,10 @@ def gemm(segs, M, N, trans_a=False, trans_b=True, bias=None, relu=False, out=Non
     ldc = _rows(out, "out")
     nb = _abi.lib().dc_gemm_workspace_bytes(M, N, ktot, int(trans_a), int(trans_b))
     ws = _workspace(nb, dev) if nb else None
+    e0 = _prof_begin()
     _abi.call("dc_gemm", arr, len(segs), int(trans_a), int(trans_b), M, N, _ptr(out), ldc, _ptr(bias), int(bool(relu)),
               int(bool(accumulate)), int(precision), _ptr(ws), nb, _stream())
+    _prof_end(e0, op="gemm", M=M, N=N, K=ktot, flops=2.0 * M * N * ktot)
     return out
 
 

@@ -46,6 +46,9 @@ typedef enum {
 
 DC_API int dc_version(void);
 DC_API const char* dc_last_error(void);
+/* Total number of kernels this library has launched in the process (relaxed atomic; bench.py's
+ * `gpu_launches`). */
+DC_API uint64_t dc_launch_count(void);
 
 /* ---------------------------------------------------------------- K5: CSR construction
  * Replaces the per-forward ``gcn_norm`` + scatter index handling of PyG

@@ -214,6 +214,6 @@ def test_abi_errors(dc):
     with pytest.raises(_abi.DcError):
         dc.ops.csr_build(torch.zeros(2, 3, dtype=torch.long), 4)          # CPU tensor: no CPU path
     with pytest.raises(_abi.DcError):
-        dc.ops.spmm(None, None, torch.zeros(4, 4).cuda())                 # null pointers -> DC_EINVAL
+        dc.ops.spmm(None, None, torch.zeros(4, 4).cuda())                 # null rowptr -> DC_EINVAL
     with pytest.raises(_abi.DcError):
         dc.ops.knn_table(torch.zeros(10, 3).cuda(), 500)                  # k too large -> DC_ENOSUP

@@ -61,7 +61,7 @@ def test_c4_single_large_mesh_knn_and_layers(dc):
     assert torch.equal(ei[1], torch.arange(N, device="cuda").repeat_interleave(k))
     assert (ei[0] != ei[1]).all()
     d = (pos[ei[0]] - pos[ei[1]]).square().sum(1).view(N, k)
-    assert (d[:, 1:] >= d[:, :-1]).all()                                          # ascending per query
+    assert (d[:, 1:] >= d[:, :-1] * (1 - 1e-5)).all()                             # ascending per query (torch's own rounding of d)
     # exactness on sampled queries against a brute-force fp64 ranking
     g = torch.Generator(device="cuda").manual_seed(0)
     for q in torch.randint(0, N, (16,), generator=g, device="cuda").tolist():

@@ -1,0 +1,154 @@
+"""CPU tests of the host-side logic: C-ABI surface, batch layout, sharding, flat-gradient exchange."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    """libdcb200.so loads and exports exactly the entry points include/dcb200.h declares."""
+    from deformcontact_b200 import _abi
+    hdr = open(os.path.join(ROOT, "include", "dcb200.h")).read()
+    declared = set(re.findall(r"DC_API[^;(]*?\b(dc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = _abi.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in dcb200.h but not exported"
+    assert declared == set(_abi.PROTOTYPES), (declared ^ set(_abi.PROTOTYPES))
+    out = subprocess.run(["nm", "-D", "--defined-only", _abi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (dc_[a-z0-9_]+)", out))
+    assert exported == declared, exported ^ declared
+    assert lib.dc_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """The product path refuses CPU tensors instead of silently computing elsewhere."""
+    import deformcontact_b200 as dc
+    from deformcontact_b200 import _abi
+    layer = dc.TAGConv(21, 8)
+    with pytest.raises(_abi.DcError):
+        layer(torch.randn(10, 21), torch.zeros(2, 0, dtype=torch.long))
+    with pytest.raises(_abi.DcError):
+        dc.knn_graph(torch.rand(10, 3), 3)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "deformcontact_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+
+
+def test_state_dict_keys_match_pyg_names():
+    import deformcontact_b200 as dc
+    m = dc.load_model()
+    keys = set(m.state_dict())
+    for k in ("conv_layers_resting.0.lins.0.weight", "conv_layers_resting.1.lins.3.weight", "conv_layers_resting.0.bias",
+              "conv_layers_rigid.1.lins.2.weight", "multihead_attention.attention_heads.1.weight", "decoder.0.weight",
+              "decoder.9.bias"):
+        assert k in keys, k
+    assert sum(p.numel() for p in m.parameters()) == 1033219
+    assert m.conv_layers_resting[0].lins[0].weight.shape == (256, 21)
+    assert m.conv_layers_rigid[0].lins[0].weight.shape == (256, 25)
+    g = dc.load_model(backbone="GATConv")
+    assert {"conv_layers_resting.0.lin.weight", "conv_layers_resting.0.att_src", "conv_layers_resting.0.att_dst",
+            "conv_layers_resting.0.bias"} <= set(g.state_dict())
+    c = dc.load_model(backbone="GCNConv")
+    assert {"conv_layers_rigid.0.lin.weight", "conv_layers_rigid.0.bias"} <= set(c.state_dict())
+
+
+def test_load_model_from_reference_config_object():
+    import deformcontact_b200 as dc
+
+    class NS:
+        pass
+    cfg = NS()
+    cfg.network = NS()
+    for k, v in dc.EVERYDAY.items():
+        setattr(cfg.network, k, v)
+    m = dc.load_model(cfg)
+    assert m.backbone == "TAGConv" and len(m.conv_layers_resting) == 2 and m.decoder[0].in_features == 768
+
+
+def test_batch_layout_matches_oracle():
+    import deformcontact_b200 as dc
+    import oracle
+    from oracle import synthetic
+    rest, _, _ = synthetic.make_batch(3, 40, 4)
+    mine = dc.Batch.from_data_list([dc.Data(x=d.x, edge_index=d.edge_index, pos=d.pos) for d in (rest[0], rest[1], rest[2])])
+    for k in ("x", "pos", "edge_index", "batch", "ptr"):
+        assert torch.equal(getattr(mine, k), getattr(rest, k)), k
+    assert torch.equal(mine[2].edge_index, rest[2].edge_index)
+    c = mine.clone()
+    c.pos += 1
+    assert not torch.equal(c.pos, mine.pos)
+
+
+def test_collate_fn_matches_reference_semantics():
+    import deformcontact_b200 as dc
+    samples = [(f"o{i}", dc.Data(pos=torch.zeros(2, 3)), dc.Data(pos=torch.ones(2, 3)),
+                {"force_vector": torch.full((3,), float(i)), "force": float(i), "path": f"p{i}"},
+                dc.Data(pos=torch.zeros(1, 3))) for i in range(3)]
+    names, rest, deformed, meta, rigid = dc.collate_fn(samples)
+    assert names == ["o0", "o1", "o2"] and len(rest) == 3 and isinstance(rest, tuple)
+    assert meta["force_vector"].shape == (3, 3) and meta["force"] == [0.0, 1.0, 2.0] and meta["path"] == ["p0", "p1", "p2"]
+
+
+def test_shard_range():
+    from deformcontact_b200 import dist
+    for n, w in ((256, 8), (10, 4), (3, 8), (7, 1)):
+        r = [dist.shard_range(n, i, w) for i in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        sizes = [b - a for a, b in r]
+        assert max(sizes) - min(sizes) <= 1
+    r = [dist.shard_range(5, i, 2, [1, 1, 1, 10, 1]) for i in range(2)]
+    assert r == [(0, 4), (4, 5)]
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as tdist
+sys.path.insert(0, os.environ["DC_ROOT"])
+from deformcontact_b200 import dist
+rank, local, world = dist.init(backend="gloo")
+torch.manual_seed(0)
+net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 1))
+flat = dist.FlatGrads(net.parameters())
+g = torch.Generator().manual_seed(1)
+X = torch.randn(12, 4, generator=g); Y = torch.randn(12, 1, generator=g)
+sizes = [5, 7]                                    # unequal shards
+lo = sum(sizes[:rank]); hi = lo + sizes[rank]
+node_share, edge_share = dist.loss_shares(sizes[rank], sizes[rank], "cpu")
+flat.zero_()
+loss = node_share * torch.nn.functional.l1_loss(net(X[lo:hi]), Y[lo:hi])
+loss.backward()
+flat.all_reduce()
+# reference: the global-mean loss on one process
+ref = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 1)); ref.load_state_dict(net.state_dict())
+torch.nn.functional.l1_loss(ref(X), Y).backward()
+refflat = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+assert torch.allclose(flat.flat, refflat, rtol=1e-5, atol=1e-7), (flat.flat, refflat)
+assert all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in net.parameters())
+f, l = dist.shard_range(10, rank, world)
+assert (f, l) == ((0, 5) if rank == 0 else (5, 10))
+tdist.barrier(); tdist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_flat_grad_allreduce_gloo_world2(tmp_path):
+    """N>1 path on CPU: world_size-2 gloo; unequal shards reproduce the global-mean gradient."""
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, DC_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
