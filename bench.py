@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--cpu-sample-graphs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-tiles", action="store_true", help="C5: fixed 2048-node tiles instead of graph-aligned tiles")
     ap.add_argument("--hidden", type=int, default=256, help="C5 sweep: feature width")
     ap.add_argument("--edges", type=float, default=10e6, help="C5 sweep: number of edges")
     return ap.parse_args()
@@ -250,7 +251,7 @@ def run_ours(args):
     roofline = None
     if hop_n:
         ach = hop_bytes / (hop_ms * 1e-3) / 1e9
-        roofline = {"kernel": "spmm_vec_kernel<32,2,4> (K1 gather/segmented-sum hop, F=256)", "bound": "hbm",
+        roofline = {"kernel": f"K1 gather/segmented-sum hop, F=256 ({ops.K1_VARIANT} variant)", "bound": "hbm",
                     "achieved": ach, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / hbm_peak,
                     "traffic": None, "launches": hop_n // args.steps, "avg_launch_ms": hop_ms / hop_n,
                     "algorithmic_bytes_per_launch": hop_bytes / hop_n,
@@ -302,10 +303,80 @@ def run_ours(args):
         tdist.destroy_process_group()
 
 
+def run_layer(args):
+    """C5 microbench: one TAGConv layer (F -> F, K=3) on a block-diagonal batch of kNN graphs with
+    `--edges` edges in total; reports MP-layer edges/sec (fwd+bwd) and the hop kernel's roofline."""
+    import deformcontact_b200 as dc
+    from deformcontact_b200 import ops
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    F, k, n = args.hidden, args.k, args.nodes
+    B = max(1, int(args.edges // (k * n)))
+    N = B * n
+    g = torch.Generator(device=dev).manual_seed(0)
+    pos = torch.rand(N, 3, generator=g, device=dev) - 0.5
+    ptr = torch.arange(B + 1, device=dev) * n
+    ei = dc.knn_graph(pos, k, ptr=ptr)
+    E = ei.shape[1]
+    x = torch.randn(N, F, generator=g, device=dev)
+    layer = dc.TAGConv(F, F).to(dev)
+    ap_tiles = None if args.no_tiles else [i * n for i in range(B + 1)]
+    G = ops.GraphCSR(ei, N, "tag", ap_tiles)
+    _ = G.t
+    out = torch.empty_like(x)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    def ev_time(fn, reps):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    hop_ms = ev_time(lambda: G.propagate(x, out=out), args.steps)
+    hop_v1_ms = ev_time(lambda: ops.spmm(G.rowptr, G.nbr, x, dis=G.dis, out=out), args.steps)
+    hop_t_ms = ev_time(lambda: G.propagate(x, transpose=True, out=out), args.steps)
+    xg = x.clone().requires_grad_(True)
+    fwd_ms = ev_time(lambda: layer(x, G, relu=True), args.steps)
+
+    def fb():
+        layer.zero_grad(set_to_none=True)
+        xg.grad = None
+        layer(xg, G, relu=True).backward(x)
+    l0 = dc._abi.lib().dc_launch_count()
+    fb_ms = ev_time(fb, args.steps)
+    launches = (dc._abi.lib().dc_launch_count() - l0) // (args.steps + max(args.warmup, 3))
+    clocks = sampler.stop()
+    hop_bytes = 8 * N * F + 4 * E + 8 * N + 4
+    ach = hop_bytes / (hop_ms * 1e-3) / 1e9
+    line = {"metric": "mp_layer_edges_per_sec", "value": E / (fb_ms * 1e-3), "unit": "edges/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": fb_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"C5 TAGConv({F},{F}) layer fwd+bwd, {B} kNN-{k} graphs x {n} nodes, N={N}, E={E}",
+                       "l2": f"hop working set {hop_bytes / 1e6:.0f} MB vs 126 MB L2; no explicit flush"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "fwd_ms": fwd_ms, "fwd_edges_per_sec": E / (fwd_ms * 1e-3),
+            "edge_traversals_per_sec_fwd_bwd": 6 * E / (fb_ms * 1e-3),
+            "hop": {"fwd_ms": hop_ms, "transpose_ms": hop_t_ms, "generic_v1_ms": hop_v1_ms, "edges_per_sec": E / (hop_ms * 1e-3)},
+            "roofline": {"kernel": f"K1 hop ({ops.K1_VARIANT})", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": hop_bytes}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "layer_c5":
+        run_layer(args)
     else:
         run_ours(args)
 

@@ -186,3 +186,203 @@ extern "C" int dc_spmm(const int32_t* rowptr, const int32_t* nbr, const float* d
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// K1 v2 — tile x feature-slice mapping with L1 reuse.
+// The v1 kernel is bound by L2->SM traffic: every edge re-fetches a full 4F-byte row through
+// L2 (E*4F bytes, k/2 x the compulsory DRAM traffic; ncu r01: 4.2 GB L2->L1 for 1.07 GB DRAM).
+// Here one CTA (1024 threads, the only one resident on its SM) owns a *tile* of consecutive
+// receivers (normally one graph of the block-diagonal batch) and a 128-byte feature *slice*;
+// the slice of the tile's source rows (~2000 x 128 B) fits the SM's L1, so each row slice
+// crosses L2 once and the remaining k-1 uses hit L1.  8 lanes x float4 cover a slice; a warp
+// works on 4 receivers at once; every lane keeps 8 row gathers in flight.  Per-edge weights
+// are precomputed in CSR order (dc_edge_weights) to remove the dependent dis[nbr] gather.
+// Summation order / rounding are unchanged (sequential in CSR order, separate mul and add).
+namespace {
+__device__ __forceinline__ int ld_stream_i32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+constexpr int TL_THREADS = 512;                   // x ~100 registers: exactly one CTA (one L1 working set) per SM
+constexpr int TL_BATCH = 4;                       // edges gathered per lane before accumulating (x2 float4 in flight)
+constexpr int TL_NPW = 8;                         // receivers per warp (4 lanes each)
+constexpr int TL_NPC = TL_THREADS / 32 * TL_NPW;  // receivers per CTA iteration
+
+__device__ __forceinline__ void acc_mul_add(float4& acc, float w, const float4& v) {
+  acc.x = __fadd_rn(acc.x, __fmul_rn(w, v.x));
+  acc.y = __fadd_rn(acc.y, __fmul_rn(w, v.y));
+  acc.z = __fadd_rn(acc.z, __fmul_rn(w, v.z));
+  acc.w = __fadd_rn(acc.w, __fmul_rn(w, v.w));
+}
+
+// four edges held one per lane of the 4-lane group: gather 2 x 2 float4 at a time, accumulate in order
+template <bool FULL>
+__device__ __forceinline__ void gather4(const float* __restrict__ hcol, unsigned ldh, bool act0, bool act1, int nb,
+                                        float wv, int cnt, float4& acc0, float4& acc1) {
+#pragma unroll
+  for (int p = 0; p < 4; p += TL_BATCH) {
+    float4 v0[TL_BATCH], v1[TL_BATCH];
+    float wj[TL_BATCH];
+#pragma unroll
+    for (int u = 0; u < TL_BATCH; ++u) {
+      const unsigned src = (unsigned)__shfl_sync(0xffffffffu, nb, p + u, 4);
+      wj[u] = __shfl_sync(0xffffffffu, wv, p + u, 4);
+      const float* row = hcol + (size_t)(src * ldh);
+      if (p + u < cnt) {
+        if (FULL || act0) v0[u] = ldg4(row);
+        if (FULL || act1) v1[u] = ldg4(row + 16);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < TL_BATCH; ++u) {
+      if (p + u < cnt) {
+        if (FULL || act0) acc_mul_add(acc0, wj[u], v0[u]);
+        if (FULL || act1) acc_mul_add(acc1, wj[u], v1[u]);
+      }
+    }
+  }
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(TL_THREADS, 1)
+spmm_tiled_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr, const float* __restrict__ w,
+                  const float* __restrict__ self_w, const float* __restrict__ h, unsigned ldh, float* __restrict__ out,
+                  unsigned ldo, const float* __restrict__ add, unsigned ldadd, int N, int F, int self_loop,
+                  const float* __restrict__ bias, int relu, const int32_t* __restrict__ tile_ptr, int n_slices,
+                  int tile_nodes) {
+  const int slice = blockIdx.x % n_slices;
+  const int tile = blockIdx.x / n_slices;
+  const int t0 = tile_ptr ? tile_ptr[tile] : tile * tile_nodes;
+  const int t1 = tile_ptr ? tile_ptr[tile + 1] : min(N, t0 + tile_nodes);
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & 3;
+  const int col0 = slice * 32 + gl * 4;
+  const bool act0 = FULL || col0 < F, act1 = FULL || (col0 + 16) < F;
+  const float* __restrict__ hcol = h + col0;
+
+  // every loop below is warp-uniform (bounds are warp maxima), so all shuffles use the full mask;
+  // all element offsets are 32-bit (host checks N * ld < 2^32)
+  int node = t0 + (threadIdx.x >> 5) * TL_NPW + (lane >> 2);
+  int beg = 0, end = 0, begn = 0, endn = 0;
+  if (node < t1) { beg = ld_stream_i32(rowptr + node); end = ld_stream_i32(rowptr + node + 1); }
+  if (node + TL_NPC < t1) { begn = ld_stream_i32(rowptr + node + TL_NPC); endn = ld_stream_i32(rowptr + node + TL_NPC + 1); }
+
+  for (int wbase = t0 + (threadIdx.x >> 5) * TL_NPW; wbase < t1; wbase += TL_NPC, node += TL_NPC) {
+    const bool valid = node < t1;
+    int nb0 = 0, nb1 = 0;
+    float w0 = 0.f, w1 = 0.f;
+    if (beg + gl < end) { nb0 = ld_stream_i32(nbr + beg + gl); w0 = w ? ld_stream_f32(w + beg + gl) : 1.0f; }
+    if (beg + 4 + gl < end) { nb1 = ld_stream_i32(nbr + beg + 4 + gl); w1 = w ? ld_stream_f32(w + beg + 4 + gl) : 1.0f; }
+    int beg2 = 0, end2 = 0;   // row pointers two iterations ahead
+    if (node + 2 * TL_NPC < t1) {
+      beg2 = ld_stream_i32(rowptr + node + 2 * TL_NPC);
+      end2 = ld_stream_i32(rowptr + node + 2 * TL_NPC + 1);
+    }
+    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+    if (add != nullptr && valid) {
+      const float* arow = add + (size_t)((unsigned)node * ldadd) + col0;
+      if (act0) acc0 = __ldcs(reinterpret_cast<const float4*>(arow));
+      if (act1) acc1 = __ldcs(reinterpret_cast<const float4*>(arow + 16));
+    }
+    const int deg = end - beg;
+    const int maxdeg = __reduce_max_sync(0xffffffffu, deg);
+    if (maxdeg > 0) gather4<FULL>(hcol, ldh, act0, act1, nb0, w0, deg, acc0, acc1);
+    if (maxdeg > 4) gather4<FULL>(hcol, ldh, act0, act1, nb1, w1, deg - 4, acc0, acc1);
+    for (int b = 8; b < maxdeg; b += 4) {
+      int nbx = 0;
+      float wx = 0.f;
+      if (beg + b + gl < end) { nbx = ld_stream_i32(nbr + beg + b + gl); wx = w ? ld_stream_f32(w + beg + b + gl) : 1.0f; }
+      gather4<FULL>(hcol, ldh, act0, act1, nbx, wx, deg - b, acc0, acc1);
+    }
+    if (valid) {
+      if (self_loop) {
+        const float ws = self_w[node];
+        const float* row = hcol + (size_t)((unsigned)node * ldh);
+        if (act0) acc_mul_add(acc0, ws, ldg4(row));
+        if (act1) acc_mul_add(acc1, ws, ldg4(row + 16));
+      }
+      if (bias) {
+        if (act0) { const float4 b4 = ldg4(bias + col0); acc0.x = __fadd_rn(acc0.x, b4.x); acc0.y = __fadd_rn(acc0.y, b4.y); acc0.z = __fadd_rn(acc0.z, b4.z); acc0.w = __fadd_rn(acc0.w, b4.w); }
+        if (act1) { const float4 b4 = ldg4(bias + col0 + 16); acc1.x = __fadd_rn(acc1.x, b4.x); acc1.y = __fadd_rn(acc1.y, b4.y); acc1.z = __fadd_rn(acc1.z, b4.z); acc1.w = __fadd_rn(acc1.w, b4.w); }
+      }
+      if (relu) {
+        acc0.x = fmaxf(acc0.x, 0.f); acc0.y = fmaxf(acc0.y, 0.f); acc0.z = fmaxf(acc0.z, 0.f); acc0.w = fmaxf(acc0.w, 0.f);
+        acc1.x = fmaxf(acc1.x, 0.f); acc1.y = fmaxf(acc1.y, 0.f); acc1.z = fmaxf(acc1.z, 0.f); acc1.w = fmaxf(acc1.w, 0.f);
+      }
+      float* orow = out + (size_t)((unsigned)node * ldo) + col0;
+      if (act0) __stcs(reinterpret_cast<float4*>(orow), acc0);
+      if (act1) __stcs(reinterpret_cast<float4*>(orow + 16), acc1);
+    }
+    beg = begn; end = endn; begn = beg2; endn = end2;
+  }
+}
+
+// w[p] = fl(dis[nbr[p]] * dis[i]) for p in row i (CSR order); self_w[i] = fl(dis[i] * dis[i])
+__global__ void edge_weights_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
+                                    const float* __restrict__ dis, int64_t N, float* __restrict__ w,
+                                    float* __restrict__ self_w) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float di = dis[i];
+  for (int p = rowptr[i]; p < rowptr[i + 1]; ++p) w[p] = __fmul_rn(dis[nbr[p]], di);
+  if (self_w) self_w[i] = __fmul_rn(di, di);
+}
+}  // namespace
+
+extern "C" int dc_edge_weights(const int32_t* rowptr, const int32_t* nbr, const float* dis, int64_t N, float* w,
+                               float* self_w, dc_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (N <= 0) return DC_OK;
+  DC_REQUIRE(rowptr && dis, DC_EINVAL, "edge_weights: null pointer");
+  edge_weights_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(rowptr, nbr, dis, N, w, self_w);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+extern "C" int dc_spmm_tiled(const int32_t* rowptr, const int32_t* nbr, const float* w, const float* self_w, const float* h,
+                             int64_t ldh, float* out, int64_t ldo, const float* add, int64_t ldadd, int64_t N, int32_t F,
+                             int self_loop, const float* bias, int relu, const int32_t* tile_ptr, int64_t n_tiles,
+                             int32_t tile_nodes, dc_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DC_REQUIRE(N >= 0 && F >= 0, DC_EINVAL, "spmm_tiled: negative size");
+  if (N == 0 || F == 0) return DC_OK;
+  DC_REQUIRE(rowptr && h && out, DC_EINVAL, "spmm_tiled: null pointer");
+  DC_REQUIRE(h != out, DC_EINVAL, "spmm_tiled: out must not alias h");
+  DC_REQUIRE(!self_loop || self_w, DC_EINVAL, "spmm_tiled: self_loop needs self_w");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  DC_REQUIRE((F % 4 == 0) && (ldh % 4 == 0) && (ldo % 4 == 0) && ldh >= F && ldo >= F && al16(h) && al16(out) &&
+                 (!add || ((ldadd % 4 == 0) && ldadd >= F && al16(add))) && (!bias || al16(bias)),
+             DC_ENOSUP, "spmm_tiled: needs F %% 4 == 0 and 16-byte aligned rows (use dc_spmm)");
+  if (!tile_ptr) {
+    DC_REQUIRE(tile_nodes > 0, DC_EINVAL, "spmm_tiled: tile_nodes must be > 0 without tile_ptr");
+    n_tiles = cdiv(N, tile_nodes);
+  }
+  DC_REQUIRE(n_tiles > 0, DC_EINVAL, "spmm_tiled: no tiles");
+  const int n_slices = (F + 31) / 32;
+  static bool carveout_set = false;  // idempotent attribute; benign if raced
+  if (!carveout_set) {
+    cudaFuncSetAttribute(spmm_tiled_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(spmm_tiled_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    carveout_set = true;
+  }
+  DC_REQUIRE(N < (1ll << 31) && (uint64_t)N * (uint64_t)ldh < (1ull << 32) && (uint64_t)N * (uint64_t)ldo < (1ull << 32) &&
+                 (!add || (uint64_t)N * (uint64_t)ldadd < (1ull << 32)),
+             DC_ENOSUP, "spmm_tiled: N*ld exceeds 32-bit element offsets (use dc_spmm)");
+  if (F % 32 == 0)
+    spmm_tiled_kernel<true><<<(unsigned)(n_tiles * n_slices), TL_THREADS, 0, st>>>(
+        rowptr, nbr, w, self_w, h, (unsigned)ldh, out, (unsigned)ldo, add, (unsigned)ldadd, (int)N, F, self_loop, bias, relu, tile_ptr,
+        n_slices, tile_nodes);
+  else
+    spmm_tiled_kernel<false><<<(unsigned)(n_tiles * n_slices), TL_THREADS, 0, st>>>(
+        rowptr, nbr, w, self_w, h, (unsigned)ldh, out, (unsigned)ldo, add, (unsigned)ldadd, (int)N, F, self_loop, bias, relu, tile_ptr,
+        n_slices, tile_nodes);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}

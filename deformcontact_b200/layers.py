@@ -38,8 +38,8 @@ class _Lin(nn.Module):
         (_glorot_ if init == "glorot" else _kaiming_uniform_linear_)(self.weight)
 
 
-def _structure(edge_index, n, mode):
-    return ops.graph_csr(edge_index, n, mode)
+def _structure(edge_index, n, mode, ptr=None):
+    return ops.graph_csr(edge_index, n, mode, ptr)
 
 
 # ------------------------------------------------------------------------------- TAGConv
@@ -60,7 +60,7 @@ class _TAGConvFn(torch.autograd.Function):
             buf = torch.empty((N, K * Fi), dtype=x.dtype, device=x.device)
             for k in range(K):
                 hk = buf[:, k * Fi:(k + 1) * Fi]
-                ops.spmm(g.rowptr, g.nbr, hs[-1], dis=g.dis, out=hk)
+                g.propagate(hs[-1], out=hk)
                 hs.append(hk)
         out = ops.gemm([(h, w) for h, w in zip(hs, weights)], N, Fo, False, True, bias=bias, relu=relu,
                        precision=precision)
@@ -88,11 +88,10 @@ class _TAGConvFn(torch.autograd.Function):
         db = ops.colsum(dout) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         dx = None
         if need_x:
-            rp, nb, _ = g.t
             gk = ops.gemm([(dout, weights[K])], N, Fi, False, False, precision=ctx.precision)
             for k in range(K - 1, -1, -1):
                 dhk = ops.gemm([(dout, weights[k])], N, Fi, False, False, precision=ctx.precision)
-                gk = ops.spmm(rp, nb, gk, dis=g.dis, add=dhk)
+                gk = g.propagate(gk, transpose=True, add=dhk)
             dx = gk
         return (dx, None, db, None, None, *dws)
 
@@ -107,8 +106,8 @@ class TAGConv(nn.Module):
         self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
         self.precision = precision
 
-    def forward(self, x, edge_index, relu=False):
-        g = _structure(edge_index, x.shape[0], "tag" if self.normalize else "plain")
+    def forward(self, x, edge_index, relu=False, ptr=None):
+        g = _structure(edge_index, x.shape[0], "tag" if self.normalize else "plain", ptr)
         return _TAGConvFn.apply(x, g, self.bias, relu, self.precision, *[l.weight for l in self.lins])
 
 
@@ -122,7 +121,7 @@ class _GCNConvFn(torch.autograd.Function):
         N = x.shape[0]
         Fo = weight.shape[0]
         xw = ops.gemm([(x, weight)], N, Fo, False, True, precision=precision)
-        out = ops.spmm(g.rowptr, g.nbr, xw, dis=g.dis, self_loop=True, bias=bias, relu=relu)
+        out = g.propagate(xw, bias=bias, relu=relu)
         ctx.g, ctx.relu, ctx.precision, ctx.has_bias = g, relu, precision, bias is not None
         ctx.save_for_backward(out if relu else None, x, weight)
         return out
@@ -137,8 +136,7 @@ class _GCNConvFn(torch.autograd.Function):
         N, Fo = dout.shape
         Fi = x.shape[1]
         db = ops.colsum(dout) if (ctx.has_bias and ctx.needs_input_grad[3]) else None
-        rp, nb, _ = g.t
-        dxw = ops.spmm(rp, nb, dout, dis=g.dis, self_loop=True)
+        dxw = g.propagate(dout, transpose=True)
         dx = ops.gemm([(dxw, weight)], N, Fi, False, False, precision=ctx.precision) if ctx.needs_input_grad[0] else None
         dw = ops.gemm([(dxw, x)], Fo, Fi, True, False, precision=ctx.precision) if ctx.needs_input_grad[2] else None
         return dx, None, dw, db, None, None
@@ -154,8 +152,8 @@ class GCNConv(nn.Module):
         self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
         self.precision = precision
 
-    def forward(self, x, edge_index, relu=False):
-        g = _structure(edge_index, x.shape[0], "gcn")
+    def forward(self, x, edge_index, relu=False, ptr=None):
+        g = _structure(edge_index, x.shape[0], "gcn", ptr)
         return _GCNConvFn.apply(x, g, self.lin.weight, self.bias, relu, self.precision)
 
 
@@ -220,7 +218,7 @@ class GATConv(nn.Module):
         self.bias = nn.Parameter(torch.zeros(heads * out_channels)) if bias else None
         self.precision = precision
 
-    def forward(self, x, edge_index, relu=False):
-        g = _structure(edge_index, x.shape[0], "gat")
+    def forward(self, x, edge_index, relu=False, ptr=None):
+        g = _structure(edge_index, x.shape[0], "gat", ptr)
         return _GATConvFn.apply(x, g, self.lin.weight, self.att_src, self.att_dst, self.bias, self.negative_slope, relu,
                                 self.precision)

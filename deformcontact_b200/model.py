@@ -84,13 +84,15 @@ class GraphNet(nn.Module):
     def encode(self, graph_resting, graph_rigid):
         """models/model.py:69-78: x = dropout(relu(conv(x, edge_index))) per layer, both branches."""
         x_resting = graph_resting.x
+        ptr_rest = _host_ptr(graph_resting) if getattr(graph_resting, "ptr", None) is not None else None
+        ptr_rigid = _host_ptr(graph_rigid) if getattr(graph_rigid, "ptr", None) is not None else None
         for conv in self.conv_layers_resting:
-            x_resting = conv(x_resting, graph_resting.edge_index, relu=True)
+            x_resting = conv(x_resting, graph_resting.edge_index, relu=True, ptr=ptr_rest)
             if self.dropout_rate > 0:
                 x_resting = F.dropout(x_resting, p=self.dropout_rate, training=self.training)
         x_rigid = graph_rigid.x
         for conv in self.conv_layers_rigid:
-            x_rigid = conv(x_rigid, graph_rigid.edge_index, relu=True)
+            x_rigid = conv(x_rigid, graph_rigid.edge_index, relu=True, ptr=ptr_rigid)
             if self.dropout_rate > 0:
                 x_rigid = F.dropout(x_rigid, p=self.dropout_rate, training=self.training)
         return x_resting, x_rigid

@@ -87,6 +87,21 @@ DC_API int dc_spmm(const int32_t* rowptr, const int32_t* nbr, const float* dis, 
             int64_t ldadd, int64_t num_nodes, int32_t F, int self_loop, const float* bias, int relu,
             dc_stream_t stream);
 
+/* K1 v2: same operation, mapped as (tile of consecutive receivers) x (128-byte feature slice)
+ * per CTA so that a tile's source-row slices are reused out of L1 instead of being re-fetched
+ * through L2 for every edge.  w [E] = per-edge weight in CSR order (dc_edge_weights; NULL -> 1),
+ * self_w [N] = self-loop weight (required when self_loop = 1).  Tiles: tile_ptr int32
+ * [n_tiles+1] of receiver offsets (e.g. graph boundaries of the block-diagonal batch, merged /
+ * split to ~2k nodes), or NULL for fixed tiles of `tile_nodes` receivers.  Needs F % 4 == 0 and
+ * 16-byte aligned rows (DC_ENOSUP otherwise -> use dc_spmm).  Same summation order and
+ * rounding as dc_spmm: results are bit-identical. */
+DC_API int dc_edge_weights(const int32_t* rowptr, const int32_t* nbr, const float* dis, int64_t num_nodes, float* w,
+                           float* self_w, dc_stream_t stream);
+DC_API int dc_spmm_tiled(const int32_t* rowptr, const int32_t* nbr, const float* w, const float* self_w, const float* h,
+                         int64_t ldh, float* out, int64_t ldo, const float* add, int64_t ldadd, int64_t num_nodes,
+                         int32_t F, int self_loop, const float* bias, int relu, const int32_t* tile_ptr,
+                         int64_t n_tiles, int32_t tile_nodes, dc_stream_t stream);
+
 /* ---------------------------------------------------------------- K2/K3: layer GEMMs
  * Replaces the Linear calls inside the PyG convs (nn/dense/linear.py; A3c in SURVEY.md).
  * C[M,N] = act( sum_{s<nseg} opA(A_s)[M,K_s] * opB(B_s)[K_s,N] + bias[N] )  (+ C if accumulate)

@@ -89,6 +89,51 @@ def test_spmm_vs_oracle_propagate(dc, F, transpose):
     assert torch.equal(out, out2), "run-to-run determinism"
 
 
+@pytest.mark.parametrize("F", [4, 24, 28, 32, 64, 100, 256, 260])
+@pytest.mark.parametrize("mode", ["tag", "gcn"])
+@pytest.mark.parametrize("tiles", ["graphs", "fixed"])
+def test_spmm_tiled_bit_identical_to_generic(dc, F, mode, tiles, monkeypatch):
+    """K1 v2 (tile x slice) == K1 v1 (generic) bit for bit, and both == oracle order."""
+    sizes = [300, 1, 2500, 40, 7000, 900]
+    n = sum(sizes)
+    g = torch.Generator().manual_seed(F)
+    eis, off = [], 0
+    for s in sizes:
+        e = torch.randint(0, s, (2, 9 * s), generator=g) + off
+        eis.append(e)
+        off += s
+    ei = torch.cat(eis, 1)
+    ptr = [0]
+    for s in sizes:
+        ptr.append(ptr[-1] + s)
+    h = torch.randn(n, F, generator=g).cuda()
+    add = torch.randn(n, F, generator=g).cuda()
+    bias = torch.randn(F, generator=g).cuda()
+    G = dc.ops.GraphCSR(ei.cuda(), n, mode, ptr if tiles == "graphs" else None)
+    monkeypatch.setattr(dc.ops, "K1_VARIANT", "tiled")
+    for tr in (False, True):
+        rp, nb, _ = G.t if tr else (G.rowptr, G.nbr, G.eid)
+        v1 = dc.ops.spmm(rp, nb, h, dis=G.dis, add=add, self_loop=(mode == "gcn"), bias=bias, relu=True)
+        v2 = G.propagate(h, transpose=tr, add=add, bias=bias, relu=True)
+        assert torch.equal(v1, v2)
+        v1 = dc.ops.spmm(rp, nb, h, dis=G.dis, self_loop=(mode == "gcn"))
+        v2 = G.propagate(h, transpose=tr)
+        assert torch.equal(v1, v2)
+    if mode == "tag":
+        _, w = oconvs.gcn_norm(ei, n, False)
+        assert torch.equal(G.propagate(h).cpu(), oconvs.propagate(h.cpu(), ei, w, n))
+
+
+def test_make_tiles():
+    from deformcontact_b200.ops import make_tiles
+    assert make_tiles([0, 2000, 4000, 6000], 6000) == [0, 2000, 4000, 6000]
+    t = make_tiles([0, 762, 1524, 2286, 3048, 3810], 3810)
+    assert t[0] == 0 and t[-1] == 3810 and all(b - a <= 2560 for a, b in zip(t, t[1:]))
+    t = make_tiles([0, 200000], 200000)
+    assert t[0] == 0 and t[-1] == 200000 and all(0 < b - a <= 2560 for a, b in zip(t, t[1:]))
+    assert make_tiles(None, 10) is None
+
+
 def test_spmm_add_bias_relu_strided(dc):
     n, e, F = 1500, 9000, 64
     ei = _rand_graph(n, e, 5)
