@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdcb200.so")
 
 DC_OK, DC_EINVAL, DC_ENOSUP, DC_ECUDA, DC_EWORKSPACE = 0, -1, -2, -3, -4
-GEMM_AUTO, GEMM_FP32, GEMM_TF32X3 = 0, 1, 2
+GEMM_AUTO, GEMM_FP32, GEMM_TF32X3, GEMM_PREFER_TC = 0, 1, 2, 3
 
 
 class DcError(RuntimeError):

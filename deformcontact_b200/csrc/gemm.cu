@@ -7,7 +7,7 @@ size_t gemm_simt_workspace_bytes(int64_t M, int64_t N, int64_t Ktot);
 int gemm_simt(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t M, int64_t N, float* C, int64_t ldc,
               const float* bias, int relu, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t st);
 bool gemm_tc_supported(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t M, int64_t N, const float* C,
-                       int64_t ldc, int accumulate);
+                       int64_t ldc, int accumulate, bool for_auto);
 size_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t Ktot, int transA, int transB);
 int gemm_tc(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t M, int64_t N, float* C, int64_t ldc,
             const float* bias, int relu, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t st);
@@ -28,13 +28,14 @@ extern "C" int dc_gemm(const dc_gemm_seg* segs, int nseg, int transA, int transB
   DC_REQUIRE(M >= 0 && N >= 0, DC_EINVAL, "gemm: negative size");
   if (M == 0 || N == 0) return DC_OK;
   DC_REQUIRE(C && ldc >= N, DC_EINVAL, "gemm: bad C / ldc");
-  DC_REQUIRE(precision >= DC_GEMM_AUTO && precision <= DC_GEMM_TF32X3, DC_EINVAL, "gemm: unknown precision %d", precision);
-  bool tc_ok = dcb::gemm_tc_supported(segs, nseg, transA, transB, M, N, C, ldc, accumulate);
+  DC_REQUIRE(precision >= DC_GEMM_AUTO && precision <= DC_GEMM_PREFER_TC, DC_EINVAL, "gemm: unknown precision %d", precision);
   if (precision == DC_GEMM_TF32X3) {
+    bool tc_ok = dcb::gemm_tc_supported(segs, nseg, transA, transB, M, N, C, ldc, accumulate, false);
     DC_REQUIRE(tc_ok, DC_ENOSUP, "gemm: shape/layout not supported by the tcgen05 path");
     return dcb::gemm_tc(segs, nseg, transA, transB, M, N, C, ldc, bias, relu, accumulate, workspace, workspace_bytes, st);
   }
-  if (precision == DC_GEMM_AUTO && tc_ok)
+  if ((precision == DC_GEMM_AUTO || precision == DC_GEMM_PREFER_TC) &&
+      dcb::gemm_tc_supported(segs, nseg, transA, transB, M, N, C, ldc, accumulate, precision == DC_GEMM_AUTO))
     return dcb::gemm_tc(segs, nseg, transA, transB, M, N, C, ldc, bias, relu, accumulate, workspace, workspace_bytes, st);
   return dcb::gemm_simt(segs, nseg, transA, transB, M, N, C, ldc, bias, relu, accumulate, workspace, workspace_bytes, st);
 }

@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _abi
-from ._abi import GEMM_AUTO, GEMM_FP32, GEMM_TF32X3  # noqa: F401
+from ._abi import GEMM_AUTO, GEMM_FP32, GEMM_TF32X3, GEMM_PREFER_TC  # noqa: F401
 
 _i32, _i64, _f32 = torch.int32, torch.int64, torch.float32
 

@@ -110,11 +110,12 @@ DC_API int dc_spmm_tiled(const int32_t* rowptr, const int32_t* nbr, const float*
  *   relu = 1 applies max(0, .) in the epilogue; bias may be NULL.
  * precision: DC_GEMM_FP32 = fp32 FFMA (SIMT); DC_GEMM_TF32X3 = tcgen05 kind::tf32 with 3-term
  * error-compensated split (fp32-class accuracy), only for transA=0, transB=1 shapes the tensor
- * path supports (otherwise DC_ENOSUP); DC_GEMM_AUTO picks.
+ * path supports (otherwise DC_ENOSUP); DC_GEMM_AUTO picks by size; DC_GEMM_PREFER_TC uses the
+ * tensor path whenever the layout allows, regardless of size, else fp32.
  * Split-K (reduction over very long K, e.g. weight gradients over all nodes) uses `workspace`
  * with a fixed-order second-stage sum.
  */
-enum { DC_GEMM_AUTO = 0, DC_GEMM_FP32 = 1, DC_GEMM_TF32X3 = 2 };
+enum { DC_GEMM_AUTO = 0, DC_GEMM_FP32 = 1, DC_GEMM_TF32X3 = 2, DC_GEMM_PREFER_TC = 3 };
 typedef struct {
   const float* A;
   int64_t lda;

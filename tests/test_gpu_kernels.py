@@ -262,3 +262,55 @@ def test_abi_errors(dc):
         dc.ops.spmm(None, None, torch.zeros(4, 4).cuda())                 # null rowptr -> DC_EINVAL
     with pytest.raises(_abi.DcError):
         dc.ops.knn_table(torch.zeros(10, 3).cuda(), 500)                  # k too large -> DC_ENOSUP
+
+
+@pytest.mark.parametrize("M,N,Ks,tb", [(128, 256, [32], True), (300, 64, [32, 64], True), (1000, 256, [256] * 4, True),
+                                       (5000, 128, [96], False), (129, 16, [64], True), (40000, 256, [256], False)])
+def test_gemm_tcgen05_3xtf32(dc, M, N, Ks, tb):
+    """tcgen05 kind::tf32 GEMM with the 3-term split: fp32-class accuracy (<= 1e-5 vs fp64)."""
+    g = torch.Generator().manual_seed(M + N)
+    As = [torch.randn(M, k, generator=g).cuda() for k in Ks]
+    Bs = [(torch.randn(N, k, generator=g) if tb else torch.randn(k, N, generator=g)).cuda() for k in Ks]
+    bias = torch.randn(N, generator=g).cuda()
+    ref = sum(a.double() @ (w.double().t() if tb else w.double()) for a, w in zip(As, Bs)) + bias.double()
+    out = dc.ops.gemm(list(zip(As, Bs)), M, N, False, tb, bias=bias, precision=dc.ops.GEMM_TF32X3)
+    assert_close(out, ref.float(), what="tcgen05 gemm")
+    out_r = dc.ops.gemm(list(zip(As, Bs)), M, N, False, tb, bias=bias, relu=True, precision=dc.ops.GEMM_TF32X3)
+    assert_close(out_r, ref.clamp_min(0).float(), what="tcgen05 gemm relu")
+    assert torch.equal(out, dc.ops.gemm(list(zip(As, Bs)), M, N, False, tb, bias=bias, precision=dc.ops.GEMM_TF32X3))
+    acc = out.clone()
+    dc.ops.gemm(list(zip(As, Bs)), M, N, False, tb, out=acc, accumulate=True, precision=dc.ops.GEMM_TF32X3)
+    assert_close(acc, (2 * ref - bias.double()).float(), what="tcgen05 gemm accumulate")
+    # strided output view
+    big = torch.zeros(M, N + 64).cuda()
+    dc.ops.gemm(list(zip(As, Bs)), M, N, False, tb, bias=bias, out=big[:, 32:32 + N], precision=dc.ops.GEMM_TF32X3)
+    assert torch.equal(big[:, 32:32 + N], out) and big[:, :32].abs().sum() == 0 and big[:, 32 + N:].abs().sum() == 0
+
+
+def test_gemm_tc_unsupported_reports_enosup(dc):
+    from deformcontact_b200 import _abi
+    A, B = torch.randn(64, 21).cuda(), torch.randn(32, 21).cuda()
+    with pytest.raises(_abi.DcError):
+        dc.ops.gemm([(A, B)], 64, 32, False, True, precision=dc.ops.GEMM_TF32X3)     # K % 32 != 0
+    out = dc.ops.gemm([(A, B)], 64, 32, False, True, precision=dc.ops.GEMM_PREFER_TC)  # falls back to fp32
+    assert_close(out, (A.double() @ B.double().t()).float(), what="prefer_tc fallback")
+
+
+@pytest.mark.parametrize("K,M,N", [(32, 128, 32), (333, 128, 32), (1000, 256, 256), (5000, 200, 64), (70001, 256, 256),
+                                   (4096, 21, 256), (100000, 256, 32)])
+def test_gemm_tcgen05_weight_gradient(dc, K, M, N):
+    """K3: C = A^T B over a long contraction, MN-major tf32 operands (SWIZZLE_128B_BASE32B), chunked split-K."""
+    g = torch.Generator().manual_seed(K + M + N)
+    A = torch.randn(K, M, generator=g).cuda()
+    B = torch.randn(K, N, generator=g).cuda()
+    if M % 4:   # lda must be a multiple of 4 floats for TMA: take a view of a padded buffer
+        Ap = torch.zeros(K, M + (4 - M % 4)).cuda()
+        Ap[:, :M] = A
+        A = Ap[:, :M]
+    ref = A.double().t() @ B.double()
+    out = dc.ops.gemm([(A, B)], M, N, True, False, precision=dc.ops.GEMM_TF32X3)
+    assert_close(out, ref.float(), what="tcgen05 dW gemm")
+    assert torch.equal(out, dc.ops.gemm([(A, B)], M, N, True, False, precision=dc.ops.GEMM_TF32X3))   # deterministic
+    acc = out.clone()
+    dc.ops.gemm([(A, B)], M, N, True, False, out=acc, accumulate=True, precision=dc.ops.GEMM_TF32X3)
+    assert_close(acc, (2 * ref).float(), what="tcgen05 dW gemm accumulate")

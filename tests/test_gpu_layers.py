@@ -134,17 +134,27 @@ def test_graphnet_golden_reference_wiring(dc, golden_dir, backbone):
 
 @pytest.mark.parametrize("attn_group", [None, 2])
 def test_graphnet_train_step_vs_oracle(dc, attn_group):
+    """Whole train step (fwd + loss + bwd) vs the oracle.  Gradients that reach the first layers pass
+    through ~10 chained GEMMs / softmaxes and column sums with heavy cancellation, so each is judged with
+    the fp64 arbiter: as close to the fp64 oracle as the fp32 oracle itself (x2), or within 1e-5."""
     rest, rigid, deformed = synthetic.make_batch(4, 300, 8)
     torch.manual_seed(0)
     ref = oracle.load_model(attn_group=attn_group)
     ours = dc.load_model(attn_group=attn_group)
     ours.load_state_dict(ref.state_dict())
     ours = ours.cuda()
+    ref64 = copy.deepcopy(ref).double()
     loss_r, l1_r, lc_r = oracle.train_step_loss(ref, rest, rigid, deformed)
     loss_r.backward()
+    to64 = lambda b: oracle.Batch.from_data_list([oracle.Data(x=b[i].x.double(), edge_index=b[i].edge_index, pos=b[i].pos.double())
+                                                  for i in range(4)])
+    loss_64, _, _ = oracle.train_step_loss(ref64, to64(rest), to64(rigid), to64(deformed))
+    loss_64.backward()
     cu = lambda b: dc.Batch.from_data_list([dc.Data(x=d.x, edge_index=d.edge_index, pos=d.pos) for d in [b[i] for i in range(4)]]).to("cuda")
     loss_o, l1_o, lc_o = dc.train_step_loss(ours, cu(rest), cu(rigid), cu(deformed))
     loss_o.backward()
     assert_close(loss_o, loss_r, what="loss")
-    for (k, pr), (_, po) in zip(ref.named_parameters(), ours.named_parameters()):
-        assert_close(po.grad, pr.grad, tol=5e-5, what=f"d{k}")   # whole-model chain (fp32 cuBLAS attention/decoder in between)
+    worst = 0.0
+    for (k, pr), (_, po), (_, p64) in zip(ref.named_parameters(), ours.named_parameters(), ref64.named_parameters()):
+        worst = max(worst, assert_close_arbiter(po.grad, pr.grad, p64.grad, what=f"d{k}"))
+    assert worst < 1e-3
