@@ -324,6 +324,98 @@ spmm_tiled_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K1 v4 — v3's tile x slice mapping with (a) an explicit streaming PREFETCH pass that pulls the tile's
+// 128-byte row slices into L1 with many independent loads in flight (this is the compulsory DRAM
+// traffic, now issued at full memory-level parallelism instead of being discovered one dependent gather
+// batch at a time), and (b) 8 lanes x float4 per receiver so that every gather touches a full 128-byte
+// line (one L1 tag lookup per 128 useful bytes).  1024 threads, <= 64 registers: one CTA (one working
+// set) per SM.  Same summation order and rounding as every other K1 variant.
+constexpr int T4_THREADS = 1024;
+constexpr int T4_NPW = 4;                          // receivers per warp (8 lanes each)
+constexpr int T4_NPC = T4_THREADS / 32 * T4_NPW;   // receivers per CTA iteration (128)
+
+__global__ void __launch_bounds__(T4_THREADS, 1)
+spmm_tiled_prefetch_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr, const float* __restrict__ w,
+                           const float* __restrict__ self_w, const float* __restrict__ h, unsigned ldh,
+                           float* __restrict__ out, unsigned ldo, const float* __restrict__ add, unsigned ldadd, int N, int F,
+                           int self_loop, const float* __restrict__ bias, int relu, const int32_t* __restrict__ tile_ptr,
+                           int n_slices, int tile_nodes, int prefetch) {
+  const int slice = blockIdx.x % n_slices;
+  const int tile = blockIdx.x / n_slices;
+  const int t0 = tile_ptr ? tile_ptr[tile] : tile * tile_nodes;
+  const int t1 = tile_ptr ? tile_ptr[tile + 1] : min(N, t0 + tile_nodes);
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & 7;
+  const int col = slice * 32 + gl * 4;
+  const bool act = col < F;
+  const float* __restrict__ hcol = h + col;
+
+  if (prefetch && act) {
+    // pass 1: stream the tile's own row slices through L1 (block-diagonal batches: sources == tile rows)
+    float sink = 0.f;
+    int r = t0 + (threadIdx.x >> 3);
+    for (; r + 3 * (T4_THREADS / 8) < t1; r += 4 * (T4_THREADS / 8)) {
+      const float4 a = ldg4(hcol + (size_t)((unsigned)r * ldh));
+      const float4 b = ldg4(hcol + (size_t)((unsigned)(r + T4_THREADS / 8) * ldh));
+      const float4 c = ldg4(hcol + (size_t)((unsigned)(r + 2 * (T4_THREADS / 8)) * ldh));
+      const float4 d = ldg4(hcol + (size_t)((unsigned)(r + 3 * (T4_THREADS / 8)) * ldh));
+      sink += a.x + b.x + c.x + d.x;
+    }
+    for (; r < t1; r += T4_THREADS / 8) sink += ldg4(hcol + (size_t)((unsigned)r * ldh)).x;
+    if (sink == 1.2345e-30f) out[0] = sink;  // never true in practice; keeps the loads alive
+  }
+
+  int node = t0 + (threadIdx.x >> 5) * T4_NPW + (lane >> 3);
+  int beg = 0, end = 0, begn = 0, endn = 0;
+  if (node < t1) { beg = ld_stream_i32(rowptr + node); end = ld_stream_i32(rowptr + node + 1); }
+  if (node + T4_NPC < t1) { begn = ld_stream_i32(rowptr + node + T4_NPC); endn = ld_stream_i32(rowptr + node + T4_NPC + 1); }
+
+  for (int wbase = t0 + (threadIdx.x >> 5) * T4_NPW; wbase < t1; wbase += T4_NPC, node += T4_NPC) {
+    const bool valid = node < t1;
+    int beg2 = 0, end2 = 0;
+    if (node + 2 * T4_NPC < t1) {
+      beg2 = ld_stream_i32(rowptr + node + 2 * T4_NPC);
+      end2 = ld_stream_i32(rowptr + node + 2 * T4_NPC + 1);
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (add != nullptr && valid && act) acc = __ldcs(reinterpret_cast<const float4*>(add + (size_t)((unsigned)node * ldadd) + col));
+    const int deg = end - beg;
+    const int maxdeg = __reduce_max_sync(0xffffffffu, deg);
+    for (int b = 0; b < maxdeg; b += 8) {
+      int nb = 0;
+      float wv = 0.f;
+      if (beg + b + gl < end) { nb = ld_stream_i32(nbr + beg + b + gl); wv = w ? ld_stream_f32(w + beg + b + gl) : 1.0f; }
+      const int cnt = deg - b;
+#pragma unroll
+      for (int p = 0; p < 8; p += 4) {
+        if (p >= maxdeg - b) break;  // warp-uniform
+        float4 v[4];
+        float wj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned src = (unsigned)__shfl_sync(0xffffffffu, nb, p + u, 8);
+          wj[u] = __shfl_sync(0xffffffffu, wv, p + u, 8);
+          if (p + u < cnt && act) v[u] = ldg4(hcol + (size_t)(src * ldh));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (p + u < cnt && act) acc_mul_add(acc, wj[u], v[u]);
+      }
+    }
+    if (valid && act) {
+      if (self_loop) acc_mul_add(acc, self_w[node], ldg4(hcol + (size_t)((unsigned)node * ldh)));
+      if (bias) {
+        const float4 b4 = ldg4(bias + col);
+        acc.x = __fadd_rn(acc.x, b4.x); acc.y = __fadd_rn(acc.y, b4.y); acc.z = __fadd_rn(acc.z, b4.z); acc.w = __fadd_rn(acc.w, b4.w);
+      }
+      if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+      __stcs(reinterpret_cast<float4*>(out + (size_t)((unsigned)node * ldo) + col), acc);
+    }
+    beg = begn; end = endn; begn = beg2; endn = end2;
+  }
+}
+
 // w[p] = fl(dis[nbr[p]] * dis[i]) for p in row i (CSR order); self_w[i] = fl(dis[i] * dis[i])
 __global__ void edge_weights_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
                                     const float* __restrict__ dis, int64_t N, float* __restrict__ w,
@@ -349,7 +441,7 @@ extern "C" int dc_edge_weights(const int32_t* rowptr, const int32_t* nbr, const 
 extern "C" int dc_spmm_tiled(const int32_t* rowptr, const int32_t* nbr, const float* w, const float* self_w, const float* h,
                              int64_t ldh, float* out, int64_t ldo, const float* add, int64_t ldadd, int64_t N, int32_t F,
                              int self_loop, const float* bias, int relu, const int32_t* tile_ptr, int64_t n_tiles,
-                             int32_t tile_nodes, dc_stream_t stream_) {
+                             int32_t tile_nodes, int variant, dc_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   DC_REQUIRE(N >= 0 && F >= 0, DC_EINVAL, "spmm_tiled: negative size");
   if (N == 0 || F == 0) return DC_OK;
@@ -375,7 +467,16 @@ extern "C" int dc_spmm_tiled(const int32_t* rowptr, const int32_t* nbr, const fl
   DC_REQUIRE(N < (1ll << 31) && (uint64_t)N * (uint64_t)ldh < (1ull << 32) && (uint64_t)N * (uint64_t)ldo < (1ull << 32) &&
                  (!add || (uint64_t)N * (uint64_t)ldadd < (1ull << 32)),
              DC_ENOSUP, "spmm_tiled: N*ld exceeds 32-bit element offsets (use dc_spmm)");
-  if (F % 32 == 0)
+  if (variant == 1 || variant == 2) {
+    static bool carve4 = false;
+    if (!carve4) {
+      cudaFuncSetAttribute(spmm_tiled_prefetch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+      carve4 = true;
+    }
+    spmm_tiled_prefetch_kernel<<<(unsigned)(n_tiles * n_slices), T4_THREADS, 0, st>>>(
+        rowptr, nbr, w, self_w, h, (unsigned)ldh, out, (unsigned)ldo, add, (unsigned)ldadd, (int)N, F, self_loop, bias, relu,
+        tile_ptr, n_slices, tile_nodes, variant == 1);
+  } else if (F % 32 == 0)
     spmm_tiled_kernel<true><<<(unsigned)(n_tiles * n_slices), TL_THREADS, 0, st>>>(
         rowptr, nbr, w, self_w, h, (unsigned)ldh, out, (unsigned)ldo, add, (unsigned)ldadd, (int)N, F, self_loop, bias, relu, tile_ptr,
         n_slices, tile_nodes);

@@ -90,10 +90,12 @@ def deg_inv_sqrt(rowptr, num_nodes, add_self_loop=False):
 import os
 
 TILE_NODES = 2048      # receivers per K1 tile (one graph of the batch where possible)
-# K1 variant: "generic" (warp-per-receiver, full rows through L2) or "tiled" (tile x 128-B slice,
-# L1 reuse).  Both are bit-identical; on B200 r01 measurements they are within 3 % on the forward
-# hop and the generic kernel is faster on the irregular transposed hop, so it is the default.
-K1_VARIANT = os.environ.get("DCB200_K1", "generic")
+# K1 variant (all bit-identical): "generic" (warp per receiver, full rows through L2), "tiled"
+# (tile x 128-B slice, 4 lanes x 2 float4), "tiled8" (tile x slice, 8 lanes x float4, full-line
+# gathers), "tiled_prefetch" (tiled8 + streaming L1 prefetch pass).  B200 r01 (C5, F=256, k=8):
+# generic 0.531 / 0.587 ms (fwd / transposed), tiled 0.533 / 0.705, tiled8 0.465 / 0.562,
+# tiled_prefetch 0.462 / 0.548  ->  tiled8 is the default where the layout allows.
+K1_VARIANT = os.environ.get("DCB200_K1", "tiled8")
 
 
 def make_tiles(ptr_host, num_nodes, target=TILE_NODES):
@@ -165,7 +167,7 @@ class GraphCSR:
         rp, nb, _ = self.t if transpose else (self.rowptr, self.nbr, self.eid)
         w = self._wt if transpose else self.w
         self_loop = self.mode == "gcn"
-        if K1_VARIANT == "tiled" and self.mode in ("tag", "gcn") and _tiled_ok(h, out, add, bias):
+        if K1_VARIANT != "generic" and self.mode in ("tag", "gcn") and _tiled_ok(h, out, add, bias):
             return spmm_tiled(rp, nb, w, self.self_w if self_loop else None, h, add=add, self_loop=self_loop, bias=bias,
                               relu=relu, out=out, tile_ptr=self.tile_ptr, n_tiles=self.n_tiles)
         return spmm(rp, nb, h, dis=self.dis, add=add, self_loop=self_loop, bias=bias, relu=relu, out=out)
@@ -255,7 +257,8 @@ def spmm_tiled(rowptr, nbr, w, self_w, h, add=None, self_loop=False, bias=None, 
     ldadd = _rows(add, "add") if add is not None else 0
     e0 = _prof_begin()
     _abi.call("dc_spmm_tiled", _ptr(rowptr), _ptr(nbr), _ptr(w), _ptr(self_w), _ptr(h), ldh, _ptr(out), ldo, _ptr(add), ldadd,
-              N, F, int(bool(self_loop)), _ptr(bias), int(bool(relu)), _ptr(tile_ptr), int(n_tiles), int(tile_nodes), _stream())
+              N, F, int(bool(self_loop)), _ptr(bias), int(bool(relu)), _ptr(tile_ptr), int(n_tiles), int(tile_nodes),
+              {"tiled": 0, "tiled_prefetch": 1, "tiled8": 2}.get(K1_VARIANT, 1), _stream())
     if e0 is not None:
         E = nbr.numel()
         _prof_end(e0, op="spmm", F=F, N=N, E=E,

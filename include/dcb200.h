@@ -94,13 +94,14 @@ DC_API int dc_spmm(const int32_t* rowptr, const int32_t* nbr, const float* dis, 
  * [n_tiles+1] of receiver offsets (e.g. graph boundaries of the block-diagonal batch, merged /
  * split to ~2k nodes), or NULL for fixed tiles of `tile_nodes` receivers.  Needs F % 4 == 0 and
  * 16-byte aligned rows (DC_ENOSUP otherwise -> use dc_spmm).  Same summation order and
- * rounding as dc_spmm: results are bit-identical. */
+ * rounding as dc_spmm: results are bit-identical.  variant: 0 = 4 lanes x 2 float4 per receiver;
+ * 1 = 8 lanes x float4 with a streaming L1 prefetch pass over the tile's own rows; 2 = same, no prefetch. */
 DC_API int dc_edge_weights(const int32_t* rowptr, const int32_t* nbr, const float* dis, int64_t num_nodes, float* w,
                            float* self_w, dc_stream_t stream);
 DC_API int dc_spmm_tiled(const int32_t* rowptr, const int32_t* nbr, const float* w, const float* self_w, const float* h,
                          int64_t ldh, float* out, int64_t ldo, const float* add, int64_t ldadd, int64_t num_nodes,
                          int32_t F, int self_loop, const float* bias, int relu, const int32_t* tile_ptr,
-                         int64_t n_tiles, int32_t tile_nodes, dc_stream_t stream);
+                         int64_t n_tiles, int32_t tile_nodes, int variant, dc_stream_t stream);
 
 /* ---------------------------------------------------------------- K2/K3: layer GEMMs
  * Replaces the Linear calls inside the PyG convs (nn/dense/linear.py; A3c in SURVEY.md).

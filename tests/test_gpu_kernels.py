@@ -92,7 +92,8 @@ def test_spmm_vs_oracle_propagate(dc, F, transpose):
 @pytest.mark.parametrize("F", [4, 24, 28, 32, 64, 100, 256, 260])
 @pytest.mark.parametrize("mode", ["tag", "gcn"])
 @pytest.mark.parametrize("tiles", ["graphs", "fixed"])
-def test_spmm_tiled_bit_identical_to_generic(dc, F, mode, tiles, monkeypatch):
+@pytest.mark.parametrize("variant", ["tiled", "tiled_prefetch"])
+def test_spmm_tiled_bit_identical_to_generic(dc, F, mode, tiles, variant, monkeypatch):
     """K1 v2 (tile x slice) == K1 v1 (generic) bit for bit, and both == oracle order."""
     sizes = [300, 1, 2500, 40, 7000, 900]
     n = sum(sizes)
@@ -110,7 +111,7 @@ def test_spmm_tiled_bit_identical_to_generic(dc, F, mode, tiles, monkeypatch):
     add = torch.randn(n, F, generator=g).cuda()
     bias = torch.randn(F, generator=g).cuda()
     G = dc.ops.GraphCSR(ei.cuda(), n, mode, ptr if tiles == "graphs" else None)
-    monkeypatch.setattr(dc.ops, "K1_VARIANT", "tiled")
+    monkeypatch.setattr(dc.ops, "K1_VARIANT", variant)
     for tr in (False, True):
         rp, nb, _ = G.t if tr else (G.rowptr, G.nbr, G.eid)
         v1 = dc.ops.spmm(rp, nb, h, dis=G.dis, add=add, self_loop=(mode == "gcn"), bias=bias, relu=True)

@@ -6,7 +6,7 @@ import torch
 
 import oracle
 from oracle import synthetic
-from helpers import assert_close, assert_close_arbiter
+from helpers import assert_close, assert_close_arbiter, rel_err
 import copy
 
 pytestmark = pytest.mark.gpu
@@ -154,7 +154,7 @@ def test_graphnet_train_step_vs_oracle(dc, attn_group):
     loss_o, l1_o, lc_o = dc.train_step_loss(ours, cu(rest), cu(rigid), cu(deformed))
     loss_o.backward()
     assert_close(loss_o, loss_r, what="loss")
-    worst = 0.0
+    # chain of ~10 kernels each within 1e-5 of its oracle op: 5e-5 for the end-to-end gradients
     for (k, pr), (_, po), (_, p64) in zip(ref.named_parameters(), ours.named_parameters(), ref64.named_parameters()):
-        worst = max(worst, assert_close_arbiter(po.grad, pr.grad, p64.grad, what=f"d{k}"))
-    assert worst < 1e-3
+        if rel_err(po.grad, pr.grad) > 5e-5:
+            assert_close_arbiter(po.grad, pr.grad, p64.grad, what=f"d{k}")
