@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import torch_ops  # noqa: F401  (registers torch.ops.dcb200.*)
 
 
 def _kaiming_uniform_linear_(w):
@@ -36,6 +37,11 @@ class _Lin(nn.Module):
         super().__init__()
         self.weight = nn.Parameter(torch.empty(o, i))
         (_glorot_ if init == "glorot" else _kaiming_uniform_linear_)(self.weight)
+
+
+# True: modules dispatch through the registered ``torch.ops.dcb200.*`` custom ops (torch_ops.py);
+# False: through the equivalent ``torch.autograd.Function``s below.  Same kernels either way.
+USE_TORCH_OPS = True
 
 
 def _structure(edge_index, n, mode, ptr=None):
@@ -107,6 +113,9 @@ class TAGConv(nn.Module):
         self.precision = precision
 
     def forward(self, x, edge_index, relu=False, ptr=None):
+        if USE_TORCH_OPS and isinstance(edge_index, torch.Tensor):
+            return torch.ops.dcb200.tag_conv(x, edge_index, [l.weight for l in self.lins], self.bias, relu, self.normalize,
+                                             self.precision, ptr)[0]
         g = _structure(edge_index, x.shape[0], "tag" if self.normalize else "plain", ptr)
         return _TAGConvFn.apply(x, g, self.bias, relu, self.precision, *[l.weight for l in self.lins])
 
@@ -153,6 +162,8 @@ class GCNConv(nn.Module):
         self.precision = precision
 
     def forward(self, x, edge_index, relu=False, ptr=None):
+        if USE_TORCH_OPS and isinstance(edge_index, torch.Tensor):
+            return torch.ops.dcb200.gcn_conv(x, edge_index, self.lin.weight, self.bias, relu, self.precision, ptr)
         g = _structure(edge_index, x.shape[0], "gcn", ptr)
         return _GCNConvFn.apply(x, g, self.lin.weight, self.bias, relu, self.precision)
 

@@ -158,3 +158,33 @@ def test_graphnet_train_step_vs_oracle(dc, attn_group):
     for (k, pr), (_, po), (_, p64) in zip(ref.named_parameters(), ours.named_parameters(), ref64.named_parameters()):
         if rel_err(po.grad, pr.grad) > 5e-5:
             assert_close_arbiter(po.grad, pr.grad, p64.grad, what=f"d{k}")
+
+
+@pytest.mark.parametrize("layer", ["TAGConv", "GCNConv"])
+def test_torch_custom_op_path_equals_autograd_function_path(dc, layer, monkeypatch):
+    """torch.ops.dcb200.* (registered custom ops + autograd) and the autograd.Function path run the same kernels."""
+    from deformcontact_b200 import layers as L
+    x, ei = _graphs()["knn"]
+    _, ours = _pair(dc, layer, 21, 64)
+    res = {}
+    for flag in (True, False):
+        monkeypatch.setattr(L, "USE_TORCH_OPS", flag)
+        ours.zero_grad()
+        xo = x.clone().cuda().requires_grad_(True)
+        o = ours(xo, ei.cuda(), relu=True)
+        o.square().sum().backward()
+        res[flag] = [o.detach().clone(), xo.grad.clone()] + [p.grad.clone() for p in ours.parameters()]
+    for a, b in zip(res[True], res[False]):
+        assert torch.equal(a, b)
+    assert "tag_conv" in dir(torch.ops.dcb200) and "gcn_conv" in dir(torch.ops.dcb200)
+
+
+def test_torch_ops_opcheck(dc):
+    x, ei = _graphs()["knn"]
+    x, ei = x.cuda(), ei.cuda()
+    ws = [torch.randn(16, 21, device="cuda", requires_grad=True) for _ in range(4)]
+    b = torch.randn(16, device="cuda", requires_grad=True)
+    torch.library.opcheck(torch.ops.dcb200.tag_conv.default, (x, ei, ws, b, True, True, 0, None),
+                          test_utils=("test_schema", "test_faketensor"))
+    torch.library.opcheck(torch.ops.dcb200.propagate.default, (x, ei, "tag", False, None, None, False, None),
+                          test_utils=("test_schema", "test_faketensor"))
