@@ -487,3 +487,73 @@ extern "C" int dc_spmm_tiled(const int32_t* rowptr, const int32_t* nbr, const fl
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// A9 (north_star's edge-MLP layer; no reference counterpart) — fused edge update.
+// With m_e = W2 relu(W1 [x_i || x_j] + b1) + b2 and sum aggregation, linearity lets the second Linear
+// move outside the sum:  a_i = W2 (sum_e relu(u_i + v_j)) + deg_i b2,  u = x W1_i^T + b1, v = x W1_j^T.
+// So the only per-edge work is  s_i = sum_{e in row i} relu(u_i + v[nbr_e])  — this kernel (mode 0) —
+// and its two backward gathers; per-edge features are never materialised.
+//   mode 0: out_i = sum_e relu(p_i + q[nbr])                         (p = u, q = v;   by-target CSR)
+//   mode 1: out_i = sum_e (p_i + q[nbr] > 0 ? r_i      : 0)          (du: r = ds;     by-target CSR)
+//   mode 2: out_i = sum_e (p_i + q[nbr] > 0 ? r[nbr]   : 0)          (dv: p = v, q = u, r = ds; by-source CSR)
+namespace {
+template <int MODE>
+__global__ void __launch_bounds__(256)
+edge_relu_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr, const float* __restrict__ p,
+                 const float* __restrict__ q, const float* __restrict__ r, float* __restrict__ out, int64_t ld, int64_t N,
+                 int nvec) {
+  // one warp per receiver; lane handles float4 columns lane, lane+32, ...
+  const int lane = threadIdx.x & 31;
+  const int64_t node = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (node >= N) return;
+  const int beg = rowptr[node], end = rowptr[node + 1];
+  for (int c = lane; c < nvec; c += 32) {
+    const float4 pi = ldg4(p + node * ld + 4 * c);
+    float4 ri = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE == 1) ri = ldg4(r + node * ld + 4 * c);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int e = beg;
+    for (; e + 1 < end; e += 2) {   // two gathers in flight
+      const int n0 = __ldg(nbr + e), n1 = __ldg(nbr + e + 1);
+      const float4 q0 = ldg4(q + (int64_t)n0 * ld + 4 * c), q1 = ldg4(q + (int64_t)n1 * ld + 4 * c);
+      float4 r0 = ri, r1 = ri;
+      if (MODE == 2) { r0 = ldg4(r + (int64_t)n0 * ld + 4 * c); r1 = ldg4(r + (int64_t)n1 * ld + 4 * c); }
+#define DC_EDGE_ACC(Q, R)                                                                  \
+  {                                                                                        \
+    const float zx = pi.x + Q.x, zy = pi.y + Q.y, zz = pi.z + Q.z, zw = pi.w + Q.w;        \
+    if (MODE == 0) { acc.x += fmaxf(zx, 0.f); acc.y += fmaxf(zy, 0.f); acc.z += fmaxf(zz, 0.f); acc.w += fmaxf(zw, 0.f); } \
+    else { acc.x += zx > 0.f ? R.x : 0.f; acc.y += zy > 0.f ? R.y : 0.f; acc.z += zz > 0.f ? R.z : 0.f; acc.w += zw > 0.f ? R.w : 0.f; } \
+  }
+      DC_EDGE_ACC(q0, r0)
+      DC_EDGE_ACC(q1, r1)
+    }
+    if (e < end) {
+      const int n0 = __ldg(nbr + e);
+      const float4 q0 = ldg4(q + (int64_t)n0 * ld + 4 * c);
+      float4 r0 = ri;
+      if (MODE == 2) r0 = ldg4(r + (int64_t)n0 * ld + 4 * c);
+      DC_EDGE_ACC(q0, r0)
+    }
+#undef DC_EDGE_ACC
+    *reinterpret_cast<float4*>(out + node * ld + 4 * c) = acc;
+  }
+}
+}  // namespace
+
+extern "C" int dc_edge_relu(const int32_t* rowptr, const int32_t* nbr, const float* p, const float* q, const float* r, float* out,
+                            int64_t ld, int64_t N, int32_t F, int mode, dc_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DC_REQUIRE(N >= 0 && F >= 0 && mode >= 0 && mode <= 2, DC_EINVAL, "edge_relu: bad arguments");
+  if (N == 0 || F == 0) return DC_OK;
+  DC_REQUIRE(rowptr && p && q && out && (mode == 0 || r), DC_EINVAL, "edge_relu: null pointer");
+  auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
+  DC_REQUIRE(F % 4 == 0 && ld % 4 == 0 && ld >= F && al16(p) && al16(q) && al16(out) && (!r || al16(r)), DC_ENOSUP,
+             "edge_relu: needs F %% 4 == 0 and 16-byte aligned rows");
+  const unsigned grid = (unsigned)cdiv(N, 8);
+  if (mode == 0) edge_relu_kernel<0><<<grid, 256, 0, st>>>(rowptr, nbr, p, q, r, out, ld, N, F / 4);
+  else if (mode == 1) edge_relu_kernel<1><<<grid, 256, 0, st>>>(rowptr, nbr, p, q, r, out, ld, N, F / 4);
+  else edge_relu_kernel<2><<<grid, 256, 0, st>>>(rowptr, nbr, p, q, r, out, ld, N, F / 4);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}

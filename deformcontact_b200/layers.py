@@ -233,3 +233,87 @@ class GATConv(nn.Module):
         g = _structure(edge_index, x.shape[0], "gat", ptr)
         return _GATConvFn.apply(x, g, self.lin.weight, self.att_src, self.att_dst, self.bias, self.negative_slope, relu,
                                 self.precision)
+
+
+# ------------------------------------------------------------------------------- MPNN (A9 extension)
+class _MPNNFn(torch.autograd.Function):
+    """Edge-MLP / scatter-sum / node-MLP residual layer (north_star wording; no reference symbol):
+        m_e = W_e2 relu(W_e1 [x_i || x_j] + b_e1) + b_e2,  a_i = sum_{e: dst = i} m_e,
+        x'_i = x_i + W_n2 relu(W_n1 [x_i || a_i] + b_n1) + b_n2.
+    The first edge Linear is split into two NODE-level GEMMs (u = x W_e1[:, :F]^T + b, v = x W_e1[:, F:]^T) and,
+    because the aggregation is a sum, the second edge Linear moves outside it:
+        a = (sum_e relu(u_i + v_j)) W_e2^T + deg * b_e2.
+    Per-edge work is one fused gather (dc_edge_relu); edge features never exist in HBM."""
+
+    @staticmethod
+    def forward(ctx, x, g, We1, be1, We2, be2, Wn1, bn1, Wn2, bn2, residual, precision):
+        x = x.contiguous()
+        N, Fi = x.shape
+        Fo = We2.shape[0]
+        u = ops.gemm([(x, We1[:, :Fi])], N, Fo, False, True, bias=be1, precision=precision)
+        v = ops.gemm([(x, We1[:, Fi:])], N, Fo, False, True, precision=precision)
+        s = ops.edge_relu(g.rowptr, g.nbr, u, v, mode=0)
+        deg = (g.rowptr[1:] - g.rowptr[:-1]).to(x.dtype).unsqueeze(1)
+        a = ops.gemm([(s, We2)], N, Fo, False, True, precision=precision)
+        a.addcmul_(deg, be2.unsqueeze(0))
+        h1 = ops.gemm([(x, Wn1[:, :Fi]), (a, Wn1[:, Fi:])], N, Fo, False, True, bias=bn1, relu=True, precision=precision)
+        if residual:
+            out = x.clone()
+            ops.gemm([(h1, Wn2)], N, Fo, False, True, bias=bn2, out=out, accumulate=True, precision=precision)
+        else:
+            out = ops.gemm([(h1, Wn2)], N, Fo, False, True, bias=bn2, precision=precision)
+        ctx.g, ctx.residual, ctx.precision = g, residual, precision
+        ctx.save_for_backward(x, u, v, s, a, h1, deg, We1, We2, Wn1, Wn2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, u, v, s, a, h1, deg, We1, We2, Wn1, Wn2 = ctx.saved_tensors
+        g, P = ctx.g, ctx.precision
+        dout = dout.contiguous()
+        N, Fi = x.shape
+        Fo = We2.shape[0]
+        G = ops.gemm
+        dh1 = ops.relu_bwd(h1, G([(dout, Wn2)], N, Fo, False, False, precision=P))
+        dWn2, dbn2 = G([(dout, h1)], Fo, Fo, True, False, precision=P), ops.colsum(dout)
+        dWn1 = torch.empty_like(Wn1)
+        G([(dh1, x)], Fo, Fi, True, False, out=dWn1[:, :Fi], precision=P)
+        G([(dh1, a)], Fo, Fo, True, False, out=dWn1[:, Fi:], precision=P)
+        dbn1 = ops.colsum(dh1)
+        dx = dout.clone() if ctx.residual else torch.zeros_like(x)
+        G([(dh1, Wn1[:, :Fi])], N, Fi, False, False, out=dx, accumulate=True, precision=P)
+        da = G([(dh1, Wn1[:, Fi:])], N, Fo, False, False, precision=P)
+        dWe2 = G([(da, s)], Fo, Fo, True, False, precision=P)
+        dbe2 = ops.colsum(da * deg)
+        ds = G([(da, We2)], N, Fo, False, False, precision=P)
+        du = ops.edge_relu(g.rowptr, g.nbr, u, v, ds, mode=1)
+        rpt, nbt, _ = g.t
+        dv = ops.edge_relu(rpt, nbt, v, u, ds, mode=2)
+        dWe1 = torch.empty_like(We1)
+        G([(du, x)], Fo, Fi, True, False, out=dWe1[:, :Fi], precision=P)
+        G([(dv, x)], Fo, Fi, True, False, out=dWe1[:, Fi:], precision=P)
+        dbe1 = ops.colsum(du)
+        G([(du, We1[:, :Fi])], N, Fi, False, False, out=dx, accumulate=True, precision=P)
+        G([(dv, We1[:, Fi:])], N, Fi, False, False, out=dx, accumulate=True, precision=P)
+        return (dx if ctx.needs_input_grad[0] else None, None, dWe1, dbe1, dWe2, dbe2, dWn1, dbn1, dWn2, dbn2, None, None)
+
+
+class MPNNLayer(nn.Module):
+    """``MPNNLayer(in, out)``; keys ``edge_mlp.{0,2}.{weight,bias}``, ``node_mlp.{0,2}.{weight,bias}``
+    (``nn.Sequential(Linear, ReLU, Linear)`` each).  Residual when ``in == out``.  Needs ``out % 4 == 0``."""
+
+    def __init__(self, in_channels, out_channels, precision=ops.GEMM_AUTO):
+        super().__init__()
+        if out_channels % 4:
+            raise NotImplementedError("MPNNLayer: out_channels must be a multiple of 4")
+        self.in_channels, self.out_channels, self.precision = in_channels, out_channels, precision
+        self.edge_mlp = nn.Sequential(nn.Linear(2 * in_channels, out_channels), nn.ReLU(), nn.Linear(out_channels, out_channels))
+        self.node_mlp = nn.Sequential(nn.Linear(in_channels + out_channels, out_channels), nn.ReLU(),
+                                      nn.Linear(out_channels, out_channels))
+
+    def forward(self, x, edge_index, relu=False, ptr=None):
+        g = _structure(edge_index, x.shape[0], "plain", ptr)
+        out = _MPNNFn.apply(x, g, self.edge_mlp[0].weight, self.edge_mlp[0].bias, self.edge_mlp[2].weight, self.edge_mlp[2].bias,
+                            self.node_mlp[0].weight, self.node_mlp[0].bias, self.node_mlp[2].weight, self.node_mlp[2].bias,
+                            self.in_channels == self.out_channels, self.precision)
+        return torch.relu(out) if relu else out

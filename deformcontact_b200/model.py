@@ -62,6 +62,7 @@ class GraphNet(nn.Module):
         self.use_mha, self.dropout_rate, self.knn_k, self.mode = use_mha, dropout_rate, knn_k, mode
         self.attn_group = attn_group
         conv_layer = (layers.GATConv if backbone == "GATConv" else layers.GCNConv if backbone == "GCNConv"
+                      else layers.MPNNLayer if backbone == "MPNN"   # extension (north_star's edge/node-MLP layer)
                       else layers.TAGConv)  # models/model.py:39 — any other string selects TAGConv
         d_rest, d_rigid = input_dims[0], input_dims[1]
         self.conv_layers_resting = nn.ModuleList()

@@ -266,6 +266,17 @@ def spmm_tiled(rowptr, nbr, w, self_w, h, add=None, self_loop=False, bias=None, 
     return out
 
 
+def edge_relu(rowptr, nbr, p, q, r=None, mode=0):
+    """Fused per-edge relu-sum and its backward gathers (A9 layer); see dc_edge_relu."""
+    N, F = p.shape
+    out = torch.empty((N, F), dtype=_f32, device=p.device)
+    for t in (p, q, r):
+        if t is not None and (t.stride(0) != F or t.stride(1) != 1):
+            raise _abi.DcError("edge_relu: operands must be contiguous [N, F]")
+    _abi.call("dc_edge_relu", _ptr(rowptr), _ptr(nbr), _ptr(p), _ptr(q), _ptr(r), _ptr(out), F, N, F, int(mode), _stream())
+    return out
+
+
 # ----------------------------------------------------------------------------- K2 / K3
 def gemm(segs, M, N, trans_a=False, trans_b=True, bias=None, relu=False, out=None, accumulate=False,
          precision=GEMM_AUTO):

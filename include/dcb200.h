@@ -103,6 +103,14 @@ DC_API int dc_spmm_tiled(const int32_t* rowptr, const int32_t* nbr, const float*
                          int32_t F, int self_loop, const float* bias, int relu, const int32_t* tile_ptr,
                          int64_t n_tiles, int32_t tile_nodes, int variant, dc_stream_t stream);
 
+/* A9 — fused edge update of the edge-MLP / node-MLP residual layer (north_star; no reference symbol):
+ *   mode 0: out_i = sum_{e in row i} relu(p_i + q[nbr_e])                 forward  (p = u, q = v, by-target CSR)
+ *   mode 1: out_i = sum_e (p_i + q[nbr_e] > 0 ? r_i : 0)                  d/du     (r = ds, by-target CSR)
+ *   mode 2: out_i = sum_e (p_i + q[nbr_e] > 0 ? r[nbr_e] : 0)             d/dv     (p = v, q = u, r = ds, by-source CSR)
+ * All matrices fp32 [N, F] with leading dimension ld; F % 4 == 0, 16-byte aligned rows. */
+DC_API int dc_edge_relu(const int32_t* rowptr, const int32_t* nbr, const float* p, const float* q, const float* r,
+                        float* out, int64_t ld, int64_t num_nodes, int32_t F, int mode, dc_stream_t stream);
+
 /* ---------------------------------------------------------------- K2/K3: layer GEMMs
  * Replaces the Linear calls inside the PyG convs (nn/dense/linear.py; A3c in SURVEY.md).
  * C[M,N] = act( sum_{s<nseg} opA(A_s)[M,K_s] * opB(B_s)[K_s,N] + bias[N] )  (+ C if accumulate)
