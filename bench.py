@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--cpu-sample-graphs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--layer", default="tag", choices=["tag", "gcn", "gat", "mpnn"], help="C5: which layer")
     ap.add_argument("--no-tiles", action="store_true", help="C5: fixed 2048-node tiles instead of graph-aligned tiles")
     ap.add_argument("--hidden", type=int, default=256, help="C5 sweep: feature width")
     ap.add_argument("--edges", type=float, default=10e6, help="C5 sweep: number of edges")
@@ -319,7 +320,7 @@ def run_layer(args):
     ei = dc.knn_graph(pos, k, ptr=ptr)
     E = ei.shape[1]
     x = torch.randn(N, F, generator=g, device=dev)
-    layer = dc.TAGConv(F, F).to(dev)
+    layer = {"tag": dc.TAGConv, "gcn": dc.GCNConv, "gat": dc.GATConv, "mpnn": dc.MPNNLayer}[args.layer](F, F).to(dev)
     ap_tiles = None if args.no_tiles else [i * n for i in range(B + 1)]
     G = ops.GraphCSR(ei, N, "tag", ap_tiles)
     _ = G.t
@@ -345,12 +346,13 @@ def run_layer(args):
     hop_v1_ms = ev_time(lambda: ops.spmm(G.rowptr, G.nbr, x, dis=G.dis, out=out), args.steps)
     hop_t_ms = ev_time(lambda: G.propagate(x, transpose=True, out=out), args.steps)
     xg = x.clone().requires_grad_(True)
-    fwd_ms = ev_time(lambda: layer(x, G, relu=True), args.steps)
+    gin = G if args.layer == "tag" else ei
+    fwd_ms = ev_time(lambda: layer(x, gin, relu=True), args.steps)
 
     def fb():
         layer.zero_grad(set_to_none=True)
         xg.grad = None
-        layer(xg, G, relu=True).backward(x)
+        layer(xg, gin, relu=True).backward(x)
     l0 = dc._abi.lib().dc_launch_count()
     fb_ms = ev_time(fb, args.steps)
     launches = (dc._abi.lib().dc_launch_count() - l0) // (args.steps + max(args.warmup, 3))
@@ -360,7 +362,7 @@ def run_layer(args):
     line = {"metric": "mp_layer_edges_per_sec", "value": E / (fb_ms * 1e-3), "unit": "edges/s", "n_gpus": 1,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": fb_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": f"C5 TAGConv({F},{F}) layer fwd+bwd, {B} kNN-{k} graphs x {n} nodes, N={N}, E={E}",
+            "config": {"workload": f"C5 {type(layer).__name__}({F},{F}) layer fwd+bwd, {B} kNN-{k} graphs x {n} nodes, N={N}, E={E}",
                        "l2": f"hop working set {hop_bytes / 1e6:.0f} MB vs 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": int(launches),
             "fwd_ms": fwd_ms, "fwd_edges_per_sec": E / (fwd_ms * 1e-3),

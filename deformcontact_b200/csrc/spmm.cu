@@ -416,6 +416,116 @@ spmm_tiled_prefetch_kernel(const int32_t* __restrict__ rowptr, const int32_t* __
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K1 v5 — shared-memory staged slices.  One 1024-thread CTA per SM owns (tile of receivers = one graph of the
+// block-diagonal batch) x (64-byte feature slice).  Phase 1 streams the tile's own row slices into shared
+// memory with cp.async (the compulsory DRAM traffic as one deep, register-free stream); phase 2 gathers from
+// shared memory (sources inside the tile; others fall back to a global load), 4 lanes x float4 per receiver,
+// 8 receivers per warp, next receiver's indices prefetched.  L2->SM traffic becomes the compulsory traffic and
+// no gather ever waits on DRAM.  Same summation order and rounding as every other K1 variant.
+constexpr int T5_THREADS = 1024;
+constexpr int T5_NPC = T5_THREADS / 4;   // receivers per CTA iteration (256)
+constexpr int T5_MAX_ROWS = 3584;        // 3584 rows x 64 B = 224 KB of shared memory
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(T5_THREADS, 1)
+spmm_smem_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr, const float* __restrict__ w,
+                 const float* __restrict__ self_w, const float* __restrict__ h, unsigned ldh, float* __restrict__ out,
+                 unsigned ldo, const float* __restrict__ add, unsigned ldadd, int N, int F, int self_loop,
+                 const float* __restrict__ bias, int relu, const int32_t* __restrict__ tile_ptr, int n_slices, int tile_nodes) {
+  extern __shared__ float4 sm4[];  // [rows][4] float4 = 64-byte row slices
+  const int slice = blockIdx.x % n_slices;
+  const int tile = blockIdx.x / n_slices;
+  const int t0 = tile_ptr ? tile_ptr[tile] : tile * tile_nodes;
+  const int t1 = tile_ptr ? tile_ptr[tile + 1] : min(N, t0 + tile_nodes);
+  const int rows = min(t1 - t0, T5_MAX_ROWS);   // staged window [t0, t0 + rows)
+  const int col_base = slice * 16;
+
+  // phase 1: stream the slice of the tile's rows into shared memory
+  for (int idx = threadIdx.x; idx < rows * 4; idx += T5_THREADS) {
+    const int r = idx >> 2, c = idx & 3;
+    const int col = col_base + c * 4;
+    if (col < F) cp_async16(&sm4[idx], h + (size_t)((unsigned)(t0 + r) * ldh) + col);
+    else sm4[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // phase 2: gather from shared memory
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & 3;
+  const int col = col_base + gl * 4;
+  const bool act = col < F;
+  const float* __restrict__ hcol = h + col;
+  int node = t0 + (threadIdx.x >> 2);
+  int beg = 0, end = 0, begn = 0, endn = 0;
+  if (node < t1) { beg = ld_stream_i32(rowptr + node); end = ld_stream_i32(rowptr + node + 1); }
+  if (node + T5_NPC < t1) { begn = ld_stream_i32(rowptr + node + T5_NPC); endn = ld_stream_i32(rowptr + node + T5_NPC + 1); }
+  // first 8 edges of the current receiver: lane gl holds edges gl and gl + 4
+  int nb0 = 0, nb1 = 0;
+  float w0 = 0.f, w1 = 0.f;
+  if (beg + gl < end) { nb0 = ld_stream_i32(nbr + beg + gl); w0 = w ? ld_stream_f32(w + beg + gl) : 1.0f; }
+  if (beg + 4 + gl < end) { nb1 = ld_stream_i32(nbr + beg + 4 + gl); w1 = w ? ld_stream_f32(w + beg + 4 + gl) : 1.0f; }
+
+  for (int wbase = t0 + (threadIdx.x >> 5) * 8; wbase < t1; wbase += T5_NPC, node += T5_NPC) {
+    const bool valid = node < t1;
+    // prefetch: next receiver's first 8 edges, and the row pointers two iterations ahead
+    int nb0n = 0, nb1n = 0, beg2 = 0, end2 = 0;
+    float w0n = 0.f, w1n = 0.f;
+    if (begn + gl < endn) { nb0n = ld_stream_i32(nbr + begn + gl); w0n = w ? ld_stream_f32(w + begn + gl) : 1.0f; }
+    if (begn + 4 + gl < endn) { nb1n = ld_stream_i32(nbr + begn + 4 + gl); w1n = w ? ld_stream_f32(w + begn + 4 + gl) : 1.0f; }
+    if (node + 2 * T5_NPC < t1) {
+      beg2 = ld_stream_i32(rowptr + node + 2 * T5_NPC);
+      end2 = ld_stream_i32(rowptr + node + 2 * T5_NPC + 1);
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (add != nullptr && valid && act) acc = __ldcs(reinterpret_cast<const float4*>(add + (size_t)((unsigned)node * ldadd) + col));
+    const int deg = end - beg;
+    const int maxdeg = __reduce_max_sync(0xffffffffu, deg);
+    for (int b = 0; b < maxdeg; b += 4) {
+      int nb;
+      float wv;
+      if (b == 0) { nb = nb0; wv = w0; }
+      else if (b == 4) { nb = nb1; wv = w1; }
+      else {
+        nb = 0; wv = 0.f;
+        if (beg + b + gl < end) { nb = ld_stream_i32(nbr + beg + b + gl); wv = w ? ld_stream_f32(w + beg + b + gl) : 1.0f; }
+      }
+      const int cnt = deg - b;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int src = __shfl_sync(0xffffffffu, nb, u, 4);
+        const float wj = __shfl_sync(0xffffffffu, wv, u, 4);
+        if (u < cnt && act) {
+          const unsigned loc = (unsigned)(src - t0);
+          const float4 v = loc < (unsigned)rows ? sm4[loc * 4 + gl] : ldg4(hcol + (size_t)((unsigned)src * ldh));
+          acc_mul_add(acc, wj, v);
+        }
+      }
+    }
+    if (valid && act) {
+      if (self_loop) {
+        const unsigned loc = (unsigned)(node - t0);
+        const float4 v = loc < (unsigned)rows ? sm4[loc * 4 + gl] : ldg4(hcol + (size_t)((unsigned)node * ldh));
+        acc_mul_add(acc, self_w[node], v);
+      }
+      if (bias) {
+        const float4 b4 = ldg4(bias + col);
+        acc.x = __fadd_rn(acc.x, b4.x); acc.y = __fadd_rn(acc.y, b4.y); acc.z = __fadd_rn(acc.z, b4.z); acc.w = __fadd_rn(acc.w, b4.w);
+      }
+      if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+      __stcs(reinterpret_cast<float4*>(out + (size_t)((unsigned)node * ldo) + col), acc);
+    }
+    beg = begn; end = endn; begn = beg2; endn = end2;
+    nb0 = nb0n; nb1 = nb1n; w0 = w0n; w1 = w1n;
+  }
+}
+
 // w[p] = fl(dis[nbr[p]] * dis[i]) for p in row i (CSR order); self_w[i] = fl(dis[i] * dis[i])
 __global__ void edge_weights_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
                                     const float* __restrict__ dis, int64_t N, float* __restrict__ w,
@@ -467,7 +577,21 @@ extern "C" int dc_spmm_tiled(const int32_t* rowptr, const int32_t* nbr, const fl
   DC_REQUIRE(N < (1ll << 31) && (uint64_t)N * (uint64_t)ldh < (1ull << 32) && (uint64_t)N * (uint64_t)ldo < (1ull << 32) &&
                  (!add || (uint64_t)N * (uint64_t)ldadd < (1ull << 32)),
              DC_ENOSUP, "spmm_tiled: N*ld exceeds 32-bit element offsets (use dc_spmm)");
-  if (variant == 1 || variant == 2) {
+  if (variant == 3) {
+    const int n_slices16 = (F + 15) / 16;
+    int max_rows = tile_nodes;   // with tile_ptr the caller guarantees tiles of at most ~2560 rows (ops.make_tiles)
+    if (tile_ptr) max_rows = T5_MAX_ROWS;
+    if (max_rows > T5_MAX_ROWS) max_rows = T5_MAX_ROWS;
+    const int smem = max_rows * 64;
+    static bool attr5 = false;
+    if (!attr5) {
+      DC_CUDA(cudaFuncSetAttribute(spmm_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_MAX_ROWS * 64));
+      attr5 = true;
+    }
+    spmm_smem_kernel<<<(unsigned)(n_tiles * n_slices16), T5_THREADS, smem, st>>>(
+        rowptr, nbr, w, self_w, h, (unsigned)ldh, out, (unsigned)ldo, add, (unsigned)ldadd, (int)N, F, self_loop, bias, relu,
+        tile_ptr, n_slices16, tile_nodes);
+  } else if (variant == 1 || variant == 2) {
     static bool carve4 = false;
     if (!carve4) {
       cudaFuncSetAttribute(spmm_tiled_prefetch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0);

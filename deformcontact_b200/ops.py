@@ -179,6 +179,8 @@ def _al16(t):
 
 def _tiled_ok(h, out, add, bias):
     F = h.shape[1]
+    if any(t is not None and t.shape[0] * t.stride(0) >= 2 ** 32 for t in (h, out, add)):
+        return False   # the tiled kernels index with 32-bit element offsets
     if F % 4 or h.dim() != 2 or h.stride(1) != 1 or h.stride(0) % 4 or not _al16(h) or not _al16(bias):
         return False
     for t in (out, add):
@@ -258,7 +260,7 @@ def spmm_tiled(rowptr, nbr, w, self_w, h, add=None, self_loop=False, bias=None, 
     e0 = _prof_begin()
     _abi.call("dc_spmm_tiled", _ptr(rowptr), _ptr(nbr), _ptr(w), _ptr(self_w), _ptr(h), ldh, _ptr(out), ldo, _ptr(add), ldadd,
               N, F, int(bool(self_loop)), _ptr(bias), int(bool(relu)), _ptr(tile_ptr), int(n_tiles), int(tile_nodes),
-              {"tiled": 0, "tiled_prefetch": 1, "tiled8": 2}.get(K1_VARIANT, 1), _stream())
+              {"tiled": 0, "tiled_prefetch": 1, "tiled8": 2, "smem": 3}.get(K1_VARIANT, 2), _stream())
     if e0 is not None:
         E = nbr.numel()
         _prof_end(e0, op="spmm", F=F, N=N, E=E,

@@ -95,7 +95,8 @@ DC_API int dc_spmm(const int32_t* rowptr, const int32_t* nbr, const float* dis, 
  * split to ~2k nodes), or NULL for fixed tiles of `tile_nodes` receivers.  Needs F % 4 == 0 and
  * 16-byte aligned rows (DC_ENOSUP otherwise -> use dc_spmm).  Same summation order and
  * rounding as dc_spmm: results are bit-identical.  variant: 0 = 4 lanes x 2 float4 per receiver;
- * 1 = 8 lanes x float4 with a streaming L1 prefetch pass over the tile's own rows; 2 = same, no prefetch. */
+ * 1 = 8 lanes x float4 with a streaming L1 prefetch pass over the tile's own rows; 2 = same, no prefetch;
+ * 3 = 64-byte slices staged in shared memory with cp.async, gathers served from shared memory. */
 DC_API int dc_edge_weights(const int32_t* rowptr, const int32_t* nbr, const float* dis, int64_t num_nodes, float* w,
                            float* self_w, dc_stream_t stream);
 DC_API int dc_spmm_tiled(const int32_t* rowptr, const int32_t* nbr, const float* w, const float* self_w, const float* h,

@@ -1,0 +1,23 @@
+"""Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import sys, torch
+sys.path.insert(0, ".")
+import deformcontact_b200 as dc
+from deformcontact_b200 import ops, synthetic
+torch.manual_seed(0)
+rest, rigid, deformed = synthetic.make_batch(2, 300, 8)
+for backbone in ("TAGConv", "GCNConv", "GATConv", "MPNN"):
+    m = dc.load_model(hidden_dim=64, backbone=backbone, attn_group=2).cuda()
+    loss, _, _ = dc.train_step_loss(m, rest, rigid, deformed)
+    loss.backward()
+pos = torch.rand(700, 3, device="cuda")
+dc.knn_graph(pos, 40); dc.radius_graph(pos, 0.2)
+x = torch.randn(rest.x.shape[0], 256, device="cuda", requires_grad=True)
+for variant in ("generic", "tiled", "tiled8", "tiled_prefetch", "smem"):
+    ops.K1_VARIANT = variant
+    ops.clear_csr_cache()
+    layer = dc.TAGConv(256, 256, precision=ops.GEMM_PREFER_TC).cuda()
+    layer(x, rest.edge_index, relu=True, ptr=rest._ptr_host).sum().backward()
+A = torch.randn(3000, 256, device="cuda"); B = torch.randn(3000, 64, device="cuda")
+ops.gemm([(A, B)], 256, 64, True, False, precision=ops.GEMM_TF32X3)
+torch.cuda.synchronize()
+print("sanitize run ok")
