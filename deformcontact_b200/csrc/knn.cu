@@ -114,6 +114,10 @@ knn_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, int64
       sx[i] = pos[3 * c]; sy[i] = pos[3 * c + 1]; sz[i] = pos[3 * c + 2];
     }
     __syncthreads();
+    // whole tile inside a query's own point cloud (the common case: one graph per CTA) -> no per-candidate range test
+    bool inside[QPW];
+#pragma unroll
+    for (int qi = 0; qi < QPW; ++qi) inside[qi] = qv[qi] && t0 >= lo[qi] && t0 + tile_n <= hi[qi];
     for (int j0 = 0; j0 < tile_n; j0 += 32) {
       const int j = j0 + lane;
       const bool inb = j < tile_n;
@@ -122,9 +126,14 @@ knn_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, int64
 #pragma unroll
       for (int qi = 0; qi < QPW; ++qi) {
         const float d = sqdist(qx[qi], qy[qi], qz[qi], px, py, pz);
-        const bool ok = inb && qv[qi] && c >= lo[qi] && c < hi[qi];
-        const unsigned long long key = ok ? (((unsigned long long)__float_as_uint(d) << 32) | (unsigned)c) : KEY_INF;
-        unsigned m = __ballot_sync(0xffffffffu, key < thresh[qi]);
+        // cheap pre-filter on the distance bits (d >= 0: unsigned order == float order); ties on the distance fall
+        // through to the exact (distance, index) compare below
+        const unsigned dbits = __float_as_uint(d);
+        const bool ok = inb && (inside[qi] || (qv[qi] && c >= lo[qi] && c < hi[qi]));
+        unsigned m = __ballot_sync(0xffffffffu, ok && dbits <= (unsigned)(thresh[qi] >> 32));
+        if (m == 0) continue;
+        const unsigned long long key = ok ? (((unsigned long long)dbits << 32) | (unsigned)c) : KEY_INF;
+        m = __ballot_sync(0xffffffffu, key < thresh[qi]);
         while (m) {
           const int b = __ffs(m) - 1;
           m &= m - 1;
