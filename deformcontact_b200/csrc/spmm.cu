@@ -526,6 +526,85 @@ spmm_smem_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K1 v6 — "lean" tile x slice kernel.  Same mapping as v4 (one 1024-thread CTA per SM owns a tile of receivers
+// x a 128-byte feature slice, 8 lanes x float4 per receiver, L1 reuse of the source-row slices) with the
+// instruction stream cut to the minimum: edges come as packed 8-byte (neighbour, weight) records that every
+// lane of a group loads itself (one uniform 64-bit load per edge: no shuffles, no warp-uniform control flow),
+// full 8-edge chunks run without predicates with all 8 row gathers issued before the first use
+// (8 x 16 B in flight per lane), one IMAD.WIDE per address.  Tails use 4-edge and 1-edge steps.
+// Same summation order and rounding as every other K1 variant (bit-identical).
+__device__ __forceinline__ int2 ldg_edge(const int2* p) { return __ldg(p); }
+
+template <bool FULL>
+__global__ void __launch_bounds__(1024, 1)
+spmm_lean_kernel(const int32_t* __restrict__ rowptr, const int2* __restrict__ edges, const float* __restrict__ self_w,
+                 const float* __restrict__ h, unsigned ldh, float* __restrict__ out, unsigned ldo,
+                 const float* __restrict__ add, unsigned ldadd, int N, int F, int self_loop, const float* __restrict__ bias,
+                 int relu, const int32_t* __restrict__ tile_ptr, int n_slices, int tile_nodes) {
+  const int slice = blockIdx.x % n_slices;
+  const int tile = blockIdx.x / n_slices;
+  const int t0 = tile_ptr ? tile_ptr[tile] : tile * tile_nodes;
+  const int t1 = tile_ptr ? tile_ptr[tile + 1] : min(N, t0 + tile_nodes);
+  const int gl = threadIdx.x & 7;
+  const int col = slice * 32 + gl * 4;
+  if (!FULL && col >= F) return;   // whole lane idle for the tail slice (no collectives below)
+  const float* __restrict__ hcol = h + col;
+  const size_t ldh_b = (size_t)ldh;
+
+  int node = t0 + (threadIdx.x >> 3);
+  int beg = 0, end = 0, begn = 0, endn = 0;
+  if (node < t1) { beg = ld_stream_i32(rowptr + node); end = ld_stream_i32(rowptr + node + 1); }
+  if (node + 128 < t1) { begn = ld_stream_i32(rowptr + node + 128); endn = ld_stream_i32(rowptr + node + 129); }
+
+  for (; node < t1; node += 128) {
+    int beg2 = 0, end2 = 0;
+    if (node + 256 < t1) { beg2 = ld_stream_i32(rowptr + node + 256); end2 = ld_stream_i32(rowptr + node + 257); }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (add != nullptr) acc = __ldcs(reinterpret_cast<const float4*>(add + (size_t)((unsigned)node * ldadd) + col));
+    int p = beg;
+    for (; p + 8 <= end; p += 8) {
+      int2 e[8];
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) e[u] = ldg_edge(edges + p + u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = ldg4(hcol + (size_t)(unsigned)e[u].x * ldh_b);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc_mul_add(acc, __int_as_float(e[u].y), v[u]);
+    }
+    if (p + 4 <= end) {
+      int2 e[4];
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) e[u] = ldg_edge(edges + p + u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ldg4(hcol + (size_t)(unsigned)e[u].x * ldh_b);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc_mul_add(acc, __int_as_float(e[u].y), v[u]);
+      p += 4;
+    }
+    for (; p < end; ++p) {
+      const int2 e = ldg_edge(edges + p);
+      acc_mul_add(acc, __int_as_float(e.y), ldg4(hcol + (size_t)(unsigned)e.x * ldh_b));
+    }
+    if (self_loop) acc_mul_add(acc, self_w[node], ldg4(hcol + (size_t)(unsigned)node * ldh_b));
+    if (bias) {
+      const float4 b4 = ldg4(bias + col);
+      acc.x = __fadd_rn(acc.x, b4.x); acc.y = __fadd_rn(acc.y, b4.y); acc.z = __fadd_rn(acc.z, b4.z); acc.w = __fadd_rn(acc.w, b4.w);
+    }
+    if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+    __stcs(reinterpret_cast<float4*>(out + (size_t)((unsigned)node * ldo) + col), acc);
+    beg = begn; end = endn; begn = beg2; endn = end2;
+  }
+}
+
+// packed (neighbour, weight bits) records in CSR order; w == NULL -> weight 1
+__global__ void pack_edges_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ w, int64_t E, int2* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < E) out[i] = make_int2(nbr[i], __float_as_int(w ? w[i] : 1.0f));
+}
+
 // w[p] = fl(dis[nbr[p]] * dis[i]) for p in row i (CSR order); self_w[i] = fl(dis[i] * dis[i])
 __global__ void edge_weights_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
                                     const float* __restrict__ dis, int64_t N, float* __restrict__ w,
@@ -537,6 +616,56 @@ __global__ void edge_weights_kernel(const int32_t* __restrict__ rowptr, const in
   if (self_w) self_w[i] = __fmul_rn(di, di);
 }
 }  // namespace
+
+extern "C" int dc_pack_edges(const int32_t* nbr, const float* w, int64_t E, void* edges_out, dc_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (E <= 0) return DC_OK;
+  DC_REQUIRE(nbr && edges_out, DC_EINVAL, "pack_edges: null pointer");
+  pack_edges_kernel<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(nbr, w, E, static_cast<int2*>(edges_out));
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+extern "C" int dc_spmm_lean(const int32_t* rowptr, const void* edges, const float* self_w, const float* h, int64_t ldh, float* out,
+                            int64_t ldo, const float* add, int64_t ldadd, int64_t N, int32_t F, int self_loop, const float* bias,
+                            int relu, const int32_t* tile_ptr, int64_t n_tiles, int32_t tile_nodes, dc_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DC_REQUIRE(N >= 0 && F >= 0, DC_EINVAL, "spmm_lean: negative size");
+  if (N == 0 || F == 0) return DC_OK;
+  DC_REQUIRE(rowptr && h && out, DC_EINVAL, "spmm_lean: null pointer");
+  DC_REQUIRE(h != out, DC_EINVAL, "spmm_lean: out must not alias h");
+  DC_REQUIRE(!self_loop || self_w, DC_EINVAL, "spmm_lean: self_loop needs self_w");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  DC_REQUIRE((F % 4 == 0) && (ldh % 4 == 0) && (ldo % 4 == 0) && ldh >= F && ldo >= F && al16(h) && al16(out) &&
+                 (!add || ((ldadd % 4 == 0) && ldadd >= F && al16(add))) && (!bias || al16(bias)) &&
+                 (!edges || (reinterpret_cast<uintptr_t>(edges) & 7) == 0),
+             DC_ENOSUP, "spmm_lean: needs F %% 4 == 0 and 16-byte aligned rows (use dc_spmm)");
+  DC_REQUIRE(N < (1ll << 31) && (uint64_t)N * (uint64_t)ldo < (1ull << 32) && (!add || (uint64_t)N * (uint64_t)ldadd < (1ull << 32)),
+             DC_ENOSUP, "spmm_lean: N*ld exceeds 32-bit element offsets (use dc_spmm)");
+  if (!tile_ptr) {
+    DC_REQUIRE(tile_nodes > 0, DC_EINVAL, "spmm_lean: tile_nodes must be > 0 without tile_ptr");
+    n_tiles = cdiv(N, tile_nodes);
+  }
+  DC_REQUIRE(n_tiles > 0, DC_EINVAL, "spmm_lean: no tiles");
+  const int n_slices = (F + 31) / 32;
+  static bool carve = false;
+  if (!carve) {
+    cudaFuncSetAttribute(spmm_lean_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(spmm_lean_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    carve = true;
+  }
+  const unsigned grid = (unsigned)(n_tiles * n_slices);
+  if (F % 32 == 0)
+    spmm_lean_kernel<true><<<grid, 1024, 0, st>>>(rowptr, static_cast<const int2*>(edges), self_w, h, (unsigned)ldh, out,
+                                                  (unsigned)ldo, add, (unsigned)ldadd, (int)N, F, self_loop, bias, relu, tile_ptr,
+                                                  n_slices, tile_nodes);
+  else
+    spmm_lean_kernel<false><<<grid, 1024, 0, st>>>(rowptr, static_cast<const int2*>(edges), self_w, h, (unsigned)ldh, out,
+                                                   (unsigned)ldo, add, (unsigned)ldadd, (int)N, F, self_loop, bias, relu, tile_ptr,
+                                                   n_slices, tile_nodes);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
 
 extern "C" int dc_edge_weights(const int32_t* rowptr, const int32_t* nbr, const float* dis, int64_t N, float* w,
                                float* self_w, dc_stream_t stream_) {

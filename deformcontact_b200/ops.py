@@ -145,8 +145,10 @@ class GraphCSR:
         self.dis = deg_inv_sqrt(self.rowptr, self.N, mode == "gcn") if mode in ("tag", "gcn") else None
         self.w, self.self_w = (edge_weights(self.rowptr, self.nbr, self.dis, self.N, mode == "gcn")
                                if self.dis is not None else (None, None))
+        self.edges = pack_edges(self.nbr, self.w) if mode in ("tag", "gcn") else None
         self._t = None
         self._wt = None
+        self._edges_t = None
         tiles = make_tiles(ptr_host, self.N)
         self.tile_ptr = (torch.tensor(tiles, dtype=_i32, device=edge_index.device) if tiles is not None else None)
         self.n_tiles = len(tiles) - 1 if tiles is not None else 0
@@ -158,6 +160,7 @@ class GraphCSR:
             self._t = csr_build(self.edge_index, self.N, 1, self.self_loops)
             if self.dis is not None:
                 self._wt = edge_weights(self._t[0], self._t[1], self.dis, self.N, False)[0]
+                self._edges_t = pack_edges(self._t[1], self._wt)
         return self._t
 
     def propagate(self, h, transpose=False, add=None, out=None, bias=None, relu=False):
@@ -167,6 +170,9 @@ class GraphCSR:
         rp, nb, _ = self.t if transpose else (self.rowptr, self.nbr, self.eid)
         w = self._wt if transpose else self.w
         self_loop = self.mode == "gcn"
+        if K1_VARIANT == "lean" and self.mode in ("tag", "gcn") and _tiled_ok(h, out, add, bias):
+            return spmm_lean(rp, self._edges_t if transpose else self.edges, self.self_w if self_loop else None, h, add=add,
+                             self_loop=self_loop, bias=bias, relu=relu, out=out, tile_ptr=self.tile_ptr, n_tiles=self.n_tiles)
         if K1_VARIANT != "generic" and self.mode in ("tag", "gcn") and _tiled_ok(h, out, add, bias):
             return spmm_tiled(rp, nb, w, self.self_w if self_loop else None, h, add=add, self_loop=self_loop, bias=bias,
                               relu=relu, out=out, tile_ptr=self.tile_ptr, n_tiles=self.n_tiles)
@@ -245,6 +251,34 @@ def edge_weights(rowptr, nbr, dis, num_nodes, want_self):
     self_w = torch.empty(num_nodes, dtype=_f32, device=dis.device) if want_self else None
     _abi.call("dc_edge_weights", _ptr(rowptr), _ptr(nbr), _ptr(dis), num_nodes, _ptr(w), _ptr(self_w), _stream())
     return w, self_w
+
+
+def pack_edges(nbr, w):
+    """int32 [E, 2] packed {neighbour, weight bits} records in CSR order; see dc_pack_edges."""
+    E = nbr.numel()
+    out = torch.empty((max(E, 1), 2), dtype=_i32, device=nbr.device)
+    _abi.call("dc_pack_edges", _ptr(nbr), _ptr(w), E, _ptr(out), _stream())
+    return out
+
+
+def spmm_lean(rowptr, edges, self_w, h, add=None, self_loop=False, bias=None, relu=False, out=None, tile_ptr=None, n_tiles=0,
+              tile_nodes=TILE_NODES):
+    """K1 v6 (lean tile x slice kernel on packed edge records); see dc_spmm_lean."""
+    _need(h, _f32, "h")
+    ldh = _rows(h, "h")
+    N, F = h.shape
+    if out is None:
+        out = torch.empty((N, F), dtype=_f32, device=h.device)
+    ldo = _rows(out, "out")
+    ldadd = _rows(add, "add") if add is not None else 0
+    e0 = _prof_begin()
+    _abi.call("dc_spmm_lean", _ptr(rowptr), _ptr(edges), _ptr(self_w), _ptr(h), ldh, _ptr(out), ldo, _ptr(add), ldadd, N, F,
+              int(bool(self_loop)), _ptr(bias), int(bool(relu)), _ptr(tile_ptr), int(n_tiles), int(tile_nodes), _stream())
+    if e0 is not None:
+        E = edges.shape[0]
+        _prof_end(e0, op="spmm", F=F, N=N, E=E,
+                  bytes=8 * N * F + 4 * E + 8 * N + 4 + (4 * N * F if add is not None else 0))
+    return out
 
 
 def spmm_tiled(rowptr, nbr, w, self_w, h, add=None, self_loop=False, bias=None, relu=False, out=None, tile_ptr=None,

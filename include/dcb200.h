@@ -104,6 +104,16 @@ DC_API int dc_spmm_tiled(const int32_t* rowptr, const int32_t* nbr, const float*
                          int32_t F, int self_loop, const float* bias, int relu, const int32_t* tile_ptr,
                          int64_t n_tiles, int32_t tile_nodes, int variant, dc_stream_t stream);
 
+/* K1 v6 ("lean"): the same tile x 128-byte-slice mapping driven by packed 8-byte edge records
+ * {int32 neighbour, fp32 weight} in CSR order (dc_pack_edges; w == NULL -> weight 1): one uniform 64-bit
+ * load per edge instead of index/weight loads + shuffles, 8 row gathers in flight per lane, no predicates on
+ * full 8-edge chunks.  Bit-identical to dc_spmm / dc_spmm_tiled. */
+DC_API int dc_pack_edges(const int32_t* nbr, const float* w, int64_t num_edges, void* edges_out, dc_stream_t stream);
+DC_API int dc_spmm_lean(const int32_t* rowptr, const void* edges, const float* self_w, const float* h, int64_t ldh,
+                        float* out, int64_t ldo, const float* add, int64_t ldadd, int64_t num_nodes, int32_t F,
+                        int self_loop, const float* bias, int relu, const int32_t* tile_ptr, int64_t n_tiles,
+                        int32_t tile_nodes, dc_stream_t stream);
+
 /* A9 — fused edge update of the edge-MLP / node-MLP residual layer (north_star; no reference symbol):
  *   mode 0: out_i = sum_{e in row i} relu(p_i + q[nbr_e])                 forward  (p = u, q = v, by-target CSR)
  *   mode 1: out_i = sum_e (p_i + q[nbr_e] > 0 ? r_i : 0)                  d/du     (r = ds, by-target CSR)

@@ -92,7 +92,7 @@ def test_spmm_vs_oracle_propagate(dc, F, transpose):
 @pytest.mark.parametrize("F", [4, 24, 28, 32, 64, 100, 256, 260])
 @pytest.mark.parametrize("mode", ["tag", "gcn"])
 @pytest.mark.parametrize("tiles", ["graphs", "fixed"])
-@pytest.mark.parametrize("variant", ["tiled", "tiled_prefetch", "smem"])
+@pytest.mark.parametrize("variant", ["tiled", "tiled_prefetch", "smem", "lean"])
 def test_spmm_tiled_bit_identical_to_generic(dc, F, mode, tiles, variant, monkeypatch):
     """K1 v2 (tile x slice) == K1 v1 (generic) bit for bit, and both == oracle order."""
     sizes = [300, 1, 2500, 40, 7000, 900]
