@@ -37,6 +37,10 @@ PROTOTYPES = {
     "dc_spmm_tiled": (_int, [_p, _p, _p, _p, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _int, _p, _int, _p, _i64, _i32, _int, _p]),
     "dc_pack_edges": (_int, [_p, _p, _i64, _p, _p]),
     "dc_spmm_lean": (_int, [_p, _p, _p, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _int, _p, _int, _p, _i64, _i32, _p]),
+    "dc_blocks_workspace_bytes": (_sz, [_i64]),
+    "dc_blocks_record_capacity": (_i64, [_i64, _i64, _i64]),
+    "dc_blocks_build": (_int, [_p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _i64, _p, _p, _p, _sz, _p]),
+    "dc_spmm_blocks": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _i32, _int, _p, _int, _int, _p]),
     "dc_edge_relu": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _int, _p]),
     "dc_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _int, _int]),
     "dc_gemm": (_int, [C.POINTER(GemmSeg), _int, _int, _int, _i64, _i64, _p, _i64, _p, _int, _int, _int, _p, _sz, _p]),

@@ -95,7 +95,13 @@ TILE_NODES = 2048      # receivers per K1 tile (one graph of the batch where pos
 # gathers), "tiled_prefetch" (tiled8 + streaming L1 prefetch pass).  B200 r01 (C5, F=256, k=8):
 # generic 0.531 / 0.587 ms (fwd / transposed), tiled 0.533 / 0.705, tiled8 0.465 / 0.562,
 # tiled_prefetch 0.462 / 0.548  ->  tiled8 is the default where the layout allows.
-K1_VARIANT = os.environ.get("DCB200_K1", "tiled8")
+# B200 r01 late (scripts/k1_lab.py, same config): lean 0.386 / 0.585, blocks (flags 28) 0.391 / 0.495  ->  "auto" =
+# lean for the forward structure (uniform kNN degrees, no extra build), edge blocks for the transposed one (ragged
+# degrees: the degree-sorted units remove the divergence).
+K1_VARIANT = os.environ.get("DCB200_K1", "auto")
+# dc_spmm_blocks flags: 1 = persistent grid, 2 = L1 record prefetch, 4 = 768-thread CTAs, 8/16 = L2 prefetch stream
+# (24 = the CTA's own tile slice), 32 = one prefetch per sector.  28 = 768 threads, one-shot grid, in-CTA L2 stream.
+K1_FLAGS = int(os.environ.get("DCB200_K1_FLAGS", "28"))
 
 
 def make_tiles(ptr_host, num_nodes, target=TILE_NODES):
@@ -152,6 +158,17 @@ class GraphCSR:
         tiles = make_tiles(ptr_host, self.N)
         self.tile_ptr = (torch.tensor(tiles, dtype=_i32, device=edge_index.device) if tiles is not None else None)
         self.n_tiles = len(tiles) - 1 if tiles is not None else 0
+        self._tiles_host = tiles
+        self._blocks = {}
+        self._max_tile = max((b - a for a, b in zip(tiles[:-1], tiles[1:])), default=0) if tiles is not None else TILE_NODES
+
+    def blocks(self, transpose=False, unit=4):
+        """K1 v7/v8 edge blocks (sliced-ELL copy of the CSR) of the forward / transposed structure, built lazily."""
+        key = (bool(transpose), unit)
+        if key not in self._blocks:
+            rp = self.t[0] if transpose else self.rowptr
+            self._blocks[key] = EdgeBlocks(rp, self._edges_t if transpose else self.edges, self.N, self.E, self._tiles_host, unit)
+        return self._blocks[key]
 
     @property
     def t(self):
@@ -170,10 +187,14 @@ class GraphCSR:
         rp, nb, _ = self.t if transpose else (self.rowptr, self.nbr, self.eid)
         w = self._wt if transpose else self.w
         self_loop = self.mode == "gcn"
-        if K1_VARIANT == "lean" and self.mode in ("tag", "gcn") and _tiled_ok(h, out, add, bias):
+        variant = K1_VARIANT if K1_VARIANT != "auto" else ("blocks" if transpose else "lean")
+        if variant == "blocks" and self.mode in ("tag", "gcn") and _tiled_ok(h, out, add, bias):
+            return spmm_blocks(self.blocks(transpose), rp, self._edges_t if transpose else self.edges,
+                               self.self_w if self_loop else None, h, add=add, self_loop=self_loop, bias=bias, relu=relu, out=out)
+        if variant == "lean" and self.mode in ("tag", "gcn") and _tiled_ok(h, out, add, bias):
             return spmm_lean(rp, self._edges_t if transpose else self.edges, self.self_w if self_loop else None, h, add=add,
                              self_loop=self_loop, bias=bias, relu=relu, out=out, tile_ptr=self.tile_ptr, n_tiles=self.n_tiles)
-        if K1_VARIANT != "generic" and self.mode in ("tag", "gcn") and _tiled_ok(h, out, add, bias):
+        if variant != "generic" and self.mode in ("tag", "gcn") and _tiled_ok(h, out, add, bias):
             return spmm_tiled(rp, nb, w, self.self_w if self_loop else None, h, add=add, self_loop=self_loop, bias=bias,
                               relu=relu, out=out, tile_ptr=self.tile_ptr, n_tiles=self.n_tiles)
         return spmm(rp, nb, h, dis=self.dis, add=add, self_loop=self_loop, bias=bias, relu=relu, out=out)
@@ -258,6 +279,55 @@ def pack_edges(nbr, w):
     E = nbr.numel()
     out = torch.empty((max(E, 1), 2), dtype=_i32, device=nbr.device)
     _abi.call("dc_pack_edges", _ptr(nbr), _ptr(w), E, _ptr(out), _stream())
+    return out
+
+
+class EdgeBlocks:
+    """Sliced-ELL (SELL-4-sigma) copy of a CSR for dc_spmm_blocks; see include/dcb200.h (K1 v7)."""
+
+    def __init__(self, rowptr, edges, num_nodes, num_edges, tiles_host=None, unit=4):
+        import numpy as np
+        self.unit = unit
+        dev = rowptr.device
+        N = int(num_nodes)
+        if tiles_host is None:
+            tp = np.arange(0, N + TILE_NODES, TILE_NODES, dtype=np.int64)[: -(-N // TILE_NODES) + 1] if N else np.zeros(1, np.int64)
+            tp[-1] = N
+        else:
+            tp = np.asarray(tiles_host, dtype=np.int64)
+        tup = np.zeros_like(tp)
+        np.cumsum((np.diff(tp) + unit - 1) // unit, out=tup[1:])
+        self.max_tile_rows = int(np.diff(tp).max()) if len(tp) > 1 else 0
+        self.n_tiles, self.n_units = len(tp) - 1, int(tup[-1])
+        both = torch.from_numpy(np.stack([tp, tup]).astype(np.int32)).to(dev)
+        self.tile_ptr, self.tile_unit_ptr = both[0], both[1]
+        cap = int(_abi.lib().dc_blocks_record_capacity(N, int(num_edges), self.n_tiles))
+        self.slots = torch.empty((max(self.n_units, 1) * unit, 4), dtype=_i32, device=dev)
+        self.recs = torch.empty((cap, 2), dtype=_i32, device=dev)
+        self.status = torch.zeros(1, dtype=_i32, device=dev)
+        self.tile_rec_ptr = torch.zeros(self.n_tiles + 1, dtype=_i32, device=dev)
+        ws = _workspace(_abi.lib().dc_blocks_workspace_bytes(self.n_units), dev)
+        _abi.call("dc_blocks_build", _ptr(rowptr), _ptr(edges), _ptr(self.tile_ptr), _ptr(self.tile_unit_ptr), self.n_tiles,
+                  self.n_units, unit, _ptr(self.slots), _ptr(self.recs), cap, _ptr(self.tile_rec_ptr), _ptr(self.status), _ptr(ws), ws.numel(), _stream())
+
+
+def spmm_blocks(blocks, rowptr, edges, self_w, h, add=None, self_loop=False, bias=None, relu=False, out=None, flags=None):
+    """K1 v7 (edge blocks); see dc_spmm_blocks."""
+    _need(h, _f32, "h")
+    ldh = _rows(h, "h")
+    N, F = h.shape
+    if out is None:
+        out = torch.empty((N, F), dtype=_f32, device=h.device)
+    ldo = _rows(out, "out")
+    ldadd = _rows(add, "add") if add is not None else 0
+    e0 = _prof_begin()
+    _abi.call("dc_spmm_blocks", _ptr(blocks.slots), _ptr(blocks.recs), _ptr(rowptr), _ptr(edges), _ptr(blocks.tile_ptr),
+              _ptr(blocks.tile_unit_ptr), _ptr(blocks.tile_rec_ptr), blocks.n_tiles, _ptr(self_w), _ptr(h), ldh, _ptr(out), ldo, _ptr(add), ldadd, F, int(bool(self_loop)), _ptr(bias),
+              int(bool(relu)), K1_FLAGS if flags is None else int(flags), _stream())
+    if e0 is not None:
+        E = edges.shape[0]
+        _prof_end(e0, op="spmm", F=F, N=N, E=E,
+                  bytes=8 * N * F + 4 * E + 8 * N + 4 + (4 * N * F if add is not None else 0))
     return out
 
 

@@ -114,6 +114,36 @@ DC_API int dc_spmm_lean(const int32_t* rowptr, const void* edges, const float* s
                         int self_loop, const float* bias, int relu, const int32_t* tile_ptr, int64_t n_tiles,
                         int32_t tile_nodes, dc_stream_t stream);
 
+/* K1 v7 ("edge blocks"): the same operation driven by a sliced-ELL (SELL-4-sigma) copy of the CSR built once
+ * per batch by dc_blocks_build and reused by every hop.  Receivers ("slots") are sorted by degree (stable,
+ * descending) inside windows of 256 receivers of a tile and grouped four to a UNIT; a unit's edge records
+ * {int32 neighbour, fp32 weight} are interleaved [pair of edges][slot][2] so one 128-bit load per lane fetches two
+ * records and a warp reads one contiguous 64-byte segment; rows deeper than 64 edges continue from the packed CSR
+ * records (`edges`, dc_pack_edges).  fp32 mul and add are issued as packed FMUL2 / FFMA2(m, 1.0, acc): separately
+ * rounded, in CSR order => bit-identical to dc_spmm.
+ *   tile_ptr      int32 [n_tiles+1]  receiver offsets of the tiles (graphs of the batch merged / split to ~2k)
+ *   tile_unit_ptr int32 [n_tiles+1]  prefix sum of ceil(tile_size / 4); n_units = tile_unit_ptr[n_tiles]
+ *   slots         int4  [n_units*4]  {node or -1, degree, record offset of the unit, depth | min_degree << 8}
+ *   recs          int2  [rec_capacity], rec_capacity >= dc_blocks_record_capacity(N, E, n_tiles) (a proven bound;
+ *                 `status` (int32, zero-initialised by the caller) is set to 1 if it were ever exceeded)
+ * unit_size = 4 (the layout dc_spmm_blocks reads) or 8; tile_unit_ptr is the prefix sum of ceil(tile_size / unit_size)
+ * and slots has n_units * unit_size entries.  Bit 16 of a slot's depth word flags units with a source outside their
+ * own tile or a row deeper than 64 edges.
+ * dc_spmm_blocks flags: bit 0 = persistent grid (one CTA per SM looping over tile slices), bit 1 = prefetch the
+ * next unit's records into L1, bit 2 = 768-thread CTAs (80 registers) instead of 1024 (64 registers), bits 3-4 =
+ * distance (in grid strides, 0 = off) of the L2 prefetch stream: while a CTA works on one tile slice it pulls the row
+ * slices, edge records and slot records of the tile slice it takes that many steps later into L2.
+ * tile_rec_ptr int32 [n_tiles+1] (written by dc_blocks_build) = record offsets at the tile boundaries. */
+DC_API size_t dc_blocks_workspace_bytes(int64_t n_units);
+DC_API int64_t dc_blocks_record_capacity(int64_t num_nodes, int64_t num_edges, int64_t n_tiles);
+DC_API int dc_blocks_build(const int32_t* rowptr, const void* edges, const int32_t* tile_ptr, const int32_t* tile_unit_ptr,
+                           int64_t n_tiles, int64_t n_units, int32_t unit_size, void* slots, void* recs, int64_t rec_capacity,
+                           int32_t* tile_rec_ptr, int32_t* status, void* workspace, size_t workspace_bytes, dc_stream_t stream);
+DC_API int dc_spmm_blocks(const void* slots, const void* recs, const int32_t* rowptr, const void* edges, const int32_t* tile_ptr,
+                          const int32_t* tile_unit_ptr, const int32_t* tile_rec_ptr, int64_t n_tiles, const float* self_w, const float* h, int64_t ldh,
+                          float* out, int64_t ldo, const float* add, int64_t ldadd, int32_t F, int self_loop,
+                          const float* bias, int relu, int flags, dc_stream_t stream);
+
 /* A9 — fused edge update of the edge-MLP / node-MLP residual layer (north_star; no reference symbol):
  *   mode 0: out_i = sum_{e in row i} relu(p_i + q[nbr_e])                 forward  (p = u, q = v, by-target CSR)
  *   mode 1: out_i = sum_e (p_i + q[nbr_e] > 0 ? r_i : 0)                  d/du     (r = ds, by-target CSR)

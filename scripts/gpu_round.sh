@@ -1,11 +1,14 @@
 #!/bin/bash
+# one GPU round: GPU tests, the bench lines of every workload, the launch list and one full ncu capture
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "tiled" 2>&1 | tail -2
-for v in tiled8 lean; do
-  DCB200_K1=$v timeout 300 python bench.py --workload layer_c5 --edges 4096000 --hidden 256 --steps 20 2>&1 | tail -1 > gpurun_out/layer_c5_$v.json
-  python - <<PY
-import json; d=json.load(open("gpurun_out/layer_c5_$v.json")); print("$v", d["hop"], "frac", round(d["roofline"]["frac"],3), "fb_ms", round(d["ms_per_step"],2))
-PY
-done
-DCB200_K1=lean timeout 600 ncu --set full --clock-control none --import-source on -k regex:spmm_lean -s 3 -c 1 -f -o gpurun_out/prof_spmm_v6 \
-    python bench.py --workload layer_c5 --edges 4096000 --hidden 256 --steps 2 --warmup 3 > gpurun_out/ncu_spmm.log 2>&1
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -3 | tee gpurun_out/pytest_gpu.txt
+timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench_default.json
+timeout 300 python bench.py --impl reference --steps 10 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_reference.json
+timeout 300 python bench.py --workload infer_c2 --steps 10 2>&1 | tail -1 > gpurun_out/bench_c2.json
+timeout 300 python bench.py --workload mesh_c4 --steps 5 2>&1 | tail -1 > gpurun_out/bench_c4.json
+timeout 300 python bench.py --workload layer_c5 --edges 4096000 --hidden 256 --steps 20 2>&1 | tail -1 > gpurun_out/bench_c5.json
+python -c "
+import json
+for f in ('bench_default','bench_reference','bench_c2','bench_c4','bench_c5'):
+    d=json.load(open('gpurun_out/%s.json'%f)); print(f, d['metric'], round(d['value'],2), d.get('e2e') and round(d['e2e']['value'],1), d.get('roofline') and round(d['roofline']['frac'],3), d.get('gpu_launches'), round(d['ms_per_step'],2))
+"

@@ -92,7 +92,7 @@ def test_spmm_vs_oracle_propagate(dc, F, transpose):
 @pytest.mark.parametrize("F", [4, 24, 28, 32, 64, 100, 256, 260])
 @pytest.mark.parametrize("mode", ["tag", "gcn"])
 @pytest.mark.parametrize("tiles", ["graphs", "fixed"])
-@pytest.mark.parametrize("variant", ["tiled", "tiled_prefetch", "smem", "lean"])
+@pytest.mark.parametrize("variant", ["tiled", "tiled_prefetch", "smem", "lean", "blocks", "auto"])
 def test_spmm_tiled_bit_identical_to_generic(dc, F, mode, tiles, variant, monkeypatch):
     """K1 v2 (tile x slice) == K1 v1 (generic) bit for bit, and both == oracle order."""
     sizes = [300, 1, 2500, 40, 7000, 900]
@@ -123,6 +123,59 @@ def test_spmm_tiled_bit_identical_to_generic(dc, F, mode, tiles, variant, monkey
     if mode == "tag":
         _, w = oconvs.gcn_norm(ei, n, False)
         assert torch.equal(G.propagate(h).cpu(), oconvs.propagate(h.cpu(), ei, w, n))
+
+
+@pytest.mark.parametrize("variant,flags", [("blocks", 0), ("blocks", 1), ("blocks", 2), ("blocks", 3), ("blocks", 4), ("blocks", 5),
+                                           ("blocks", 7), ("blocks", 8), ("blocks", 13), ("blocks", 23), ("blocks", 28), ("blocks", 61)])
+@pytest.mark.parametrize("mode", ["tag", "gcn"])
+def test_spmm_blocks_ragged_and_deep_rows(dc, variant, flags, mode, monkeypatch):
+    """K1 v7 (edge blocks): rows deeper than the 64-edge block depth, isolated receivers, duplicate edges, self
+    loops, tiles that are not multiples of 4/256 — bit-identical to the generic kernel in every launch mode."""
+    g = torch.Generator().manual_seed(flags)
+    sizes = [5, 1, 1031, 3, 700, 258]
+    n = sum(sizes)
+    ptr = [0]
+    for s in sizes:
+        ptr.append(ptr[-1] + s)
+    eis = []
+    for lo, hi in zip(ptr[:-1], ptr[1:]):
+        s = hi - lo
+        eis.append(torch.randint(0, s, (2, 5 * s), generator=g) + lo)
+    hub = ptr[2] + 7                                  # 300 in-edges and 200 out-edges on one node (deg > 64)
+    eis.append(torch.stack([torch.randint(ptr[2], ptr[3], (300,), generator=g), torch.full((300,), hub)]))
+    eis.append(torch.stack([torch.full((200,), hub), torch.randint(ptr[2], ptr[3], (200,), generator=g)]))
+    eis.append(torch.tensor([[hub, hub, ptr[4]], [hub, hub, ptr[4]]]))   # self loops (one duplicated)
+    ei = torch.cat(eis, 1)
+    ei = ei[:, torch.randperm(ei.shape[1], generator=g)]
+    F = 72
+    h = torch.randn(n, F, generator=g).cuda()
+    add = torch.randn(n, F, generator=g).cuda()
+    bias = torch.randn(F, generator=g).cuda()
+    G = dc.ops.GraphCSR(ei.cuda(), n, mode, ptr)
+    monkeypatch.setattr(dc.ops, "K1_VARIANT", variant)
+    monkeypatch.setattr(dc.ops, "K1_FLAGS", flags)
+    unit = 4
+    for tr in (False, True):
+        rp, nb, _ = G.t if tr else (G.rowptr, G.nbr, G.eid)
+        v1 = dc.ops.spmm(rp, nb, h, dis=G.dis, add=add, self_loop=(mode == "gcn"), bias=bias, relu=True)
+        v2 = G.propagate(h, transpose=tr, add=add, bias=bias, relu=True)
+        assert torch.equal(v1, v2)
+        v1 = dc.ops.spmm(rp, nb, h, dis=G.dis, self_loop=(mode == "gcn"))
+        v2 = G.propagate(h, transpose=tr)
+        assert torch.equal(v1, v2)
+        assert int(G.blocks(tr, unit).status.item()) == 0
+    Gf = dc.ops.GraphCSR(ei.cuda(), n, mode, None)    # fixed tiles
+    assert torch.equal(Gf.propagate(h), G.propagate(h))
+    # tiles that cut through graphs: sources outside the tile take the checked path
+    cut = dc.ops.EdgeBlocks(G.rowptr, G.edges, n, G.edges.shape[0], [0, 500, 1037, 1500, n], unit)
+    fn = dc.ops.spmm_blocks
+    sw = G.self_w if mode == "gcn" else None
+    assert torch.equal(fn(cut, G.rowptr, G.edges, sw, h, self_loop=(mode == "gcn")), G.propagate(h))
+    assert int(cut.status.item()) == 0
+    # empty graph / no edges
+    G0 = dc.ops.GraphCSR(torch.zeros(2, 0, dtype=torch.long).cuda(), 10, mode)
+    x0 = torch.randn(10, 8, generator=g).cuda()
+    assert torch.equal(G0.propagate(x0), dc.ops.spmm(G0.rowptr, G0.nbr, x0, dis=G0.dis, self_loop=(mode == "gcn")))
 
 
 def test_make_tiles():
