@@ -194,7 +194,6 @@ spmm_blk_kernel(const int4* __restrict__ slots, const int4* __restrict__ recs, c
     if (unit >= u1) continue;          // warp-uniform
     const char* __restrict__ hb = reinterpret_cast<const char*>(h + col);
     int4 s = ld_slot(slots + (size_t)unit * 4 + g);
-
     for (; unit < u1; unit += UPC) {
       const int4 sn = unit + UPC < u1 ? ld_slot(slots + (size_t)(unit + UPC) * 4 + g) : pad;   // slot record one unit ahead
       const int node = s.x, deg = s.y;

@@ -1,14 +1,3 @@
 #!/bin/bash
-# one GPU round: GPU tests, the bench lines of every workload, the launch list and one full ncu capture
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -3 | tee gpurun_out/pytest_gpu.txt
-timeout 600 python bench.py 2>&1 | tail -1 > gpurun_out/bench_default.json
-timeout 300 python bench.py --impl reference --steps 10 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_reference.json
-timeout 300 python bench.py --workload infer_c2 --steps 10 2>&1 | tail -1 > gpurun_out/bench_c2.json
-timeout 300 python bench.py --workload mesh_c4 --steps 5 2>&1 | tail -1 > gpurun_out/bench_c4.json
-timeout 300 python bench.py --workload layer_c5 --edges 4096000 --hidden 256 --steps 20 2>&1 | tail -1 > gpurun_out/bench_c5.json
-python -c "
-import json
-for f in ('bench_default','bench_reference','bench_c2','bench_c4','bench_c5'):
-    d=json.load(open('gpurun_out/%s.json'%f)); print(f, d['metric'], round(d['value'],2), d.get('e2e') and round(d['e2e']['value'],1), d.get('roofline') and round(d['roofline']['frac'],3), d.get('gpu_launches'), round(d['ms_per_step'],2))
-"
+for n in 1000 1500 1750 2000 2500; do echo "== nodes $n"; timeout 300 python scripts/k1_lab.py --nodes $n --graphs $((512000/n)) --variants lean,blocks:4,blocks:28 2>&1 | tail -3; done
