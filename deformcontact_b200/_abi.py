@@ -46,6 +46,8 @@ PROTOTYPES = {
     "dc_gemm": (_int, [C.POINTER(GemmSeg), _int, _int, _int, _i64, _i64, _p, _i64, _p, _int, _int, _int, _p, _sz, _p]),
     "dc_colsum_workspace_bytes": (_sz, [_i64, _i64]),
     "dc_colsum": (_int, [_p, _i64, _i64, _i64, _p, _p, _sz, _p]),
+    "dc_softmax_rows": (_int, [_p, _i64, _i64, _i64, _p]),
+    "dc_softmax_bwd_rows": (_int, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "dc_relu_bwd": (_int, [_p, _p, _p, _i64, _p]),
     "dc_knn": (_int, [_p, _p, _i64, _i64, _i32, _int, _p, _p]),
     "dc_radius": (_int, [_p, _p, _i64, _i64, _f32, _i32, _int, _p, _p, _p]),

@@ -55,6 +55,9 @@ struct TcParams {
   int relu, accumulate;
   int m_tiles;
   int drain_kb;   // main-accumulator chain length in k-blocks
+  int n_chunks;   // output columns are covered in chunks of TC_MAX_N (N > 256: score-matrix shaped GEMMs)
+  int n_mma;      // MMA N per chunk (N itself when N <= chunk width, else the chunk width with TMA zero fill past N)
+  int n_chunk;    // chunk width: 256, or 128 when that is what it takes to give every SM a tile
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -154,7 +157,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int N = p.N;
-  const uint32_t b_bytes = (uint32_t)N * TC_BK * 4;
+  const int total_tiles = p.m_tiles * p.n_chunks;   // tile t -> (m tile t / n_chunks, column chunk t % n_chunks)
+  const uint32_t b_bytes = (uint32_t)p.n_mma * TC_BK * 4;
   const uint32_t stage_tx = A_TILE_BYTES + 2 * b_bytes;
 
   if (warp == 0) {
@@ -162,8 +166,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (lane == 0) {
       const CUtensorMap* maps[4] = {&mapA0, &mapA1, &mapA2, &mapA3};
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-        const int m0 = tile * TC_BM;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_chunks) * TC_BM;
+        const int n0 = (tile % p.n_chunks) * p.n_chunk;
         int kb = 0;
         for (int s = 0; s < p.nseg; ++s) {
           for (int j = 0; j < p.kb_seg[s]; ++j, ++kb, ++it) {
@@ -173,8 +178,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const uint32_t sbase = base + st * STAGE_BYTES;
             mbar_expect_tx(full_bar(st), stage_tx);
             tma_load_2d(sbase, maps[s], full_bar(st), j * TC_BK, m0);
-            tma_load_2d(sbase + 2 * A_TILE_BYTES, &mapBhi, full_bar(st), kb * TC_BK, 0);
-            tma_load_2d(sbase + 2 * A_TILE_BYTES + B_TILE_BYTES, &mapBlo, full_bar(st), kb * TC_BK, 0);
+            tma_load_2d(sbase + 2 * A_TILE_BYTES, &mapBhi, full_bar(st), kb * TC_BK, n0);
+            tma_load_2d(sbase + 2 * A_TILE_BYTES + B_TILE_BYTES, &mapBlo, full_bar(st), kb * TC_BK, n0);
           }
         }
       }
@@ -182,10 +187,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int it = 0, dcount = 0;
       const uint32_t d_main = tmem_base, d_cross = tmem_base + TC_MAX_N;
-      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         for (int kb0 = 0; kb0 < p.kb_total; kb0 += p.drain_kb, ++dcount) {
           const int kb1 = min(p.kb_total, kb0 + p.drain_kb);
           mbar_wait(tempty_bar(0), (dcount & 1) ^ 1);
@@ -216,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     // ------------------------------------------------------------------ split warps: A -> A_hi (in place), A_lo
     const int t = threadIdx.x - 256;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < p.kb_total; ++kb, ++it) {
         const int st = it % TC_STAGES;
         const uint32_t ph = (it / TC_STAGES) & 1;
@@ -247,15 +252,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                         (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     int dcount = 0;
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+     const int n0 = (tile % p.n_chunks) * p.n_chunk;
+     const int ncols = min(p.n_chunk, N - n0);
      for (int kb0 = 0; kb0 < p.kb_total; kb0 += p.drain_kb, ++dcount) {
       const bool first_drain = kb0 == 0, last_drain = kb0 + p.drain_kb >= p.kb_total;
       const bool acc_c = first_drain ? (p.accumulate != 0) : true;   // later drains add onto this tile's partial C
       const bool do_relu = last_drain && p.relu;
       mbar_wait(tfull_bar(0), dcount & 1);
       tc_fence_after();
-      const int row0 = tile * TC_BM + q * 32;
-      for (int c = 0; c < N; c += 32) {
+      const int row0 = (tile / p.n_chunks) * TC_BM + q * 32;
+      for (int c = 0; c < ncols; c += 32) {
         uint32_t r[32], x[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
 #define DC_TMEM_LD32(R, ADDR)                                                                                            \
@@ -288,7 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
         __syncwarp();
         const int c4 = (lane & 7) * 4;
-        const int col = c + c4;
+        const int col = n0 + c + c4;
         if (vec_ok && col + 3 < N) {
           const float4 bv = (p.bias && first_drain) ? *reinterpret_cast<const float4*>(p.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -635,11 +642,13 @@ bool gemm_tc_supported(const dc_gemm_seg* segs, int nseg, int transA, int transB
   // DC_GEMM_TF32X3 / DC_GEMM_PREFER_TC still select it explicitly.
   if (transA) return !for_auto && tn_supported(segs, nseg, transB, M, N);
   if (nseg < 1 || nseg > 4) return false;
-  if (N % 16 != 0 || N < 16 || N > TC_MAX_N) return false;
+  // N <= 256: one chunk, MMA N = N (multiple of 16).  N > 256: chunks of 256 columns, the last one zero-filled by TMA.
+  if (N < 16 || (N <= TC_MAX_N && N % 16 != 0) || N >= (1ll << 24)) return false;
   if (M < 1 || M >= (1ll << 31)) return false;
   int64_t ktot = 0;
   for (int s = 0; s < nseg; ++s) {
-    if (segs[s].K <= 0 || segs[s].K % TC_BK != 0) return false;
+    // a single segment may have any K % 4 == 0 (TMA zero-fills the last k-block of A and of the packed B)
+    if (segs[s].K <= 0 || (nseg > 1 ? segs[s].K % TC_BK != 0 : segs[s].K % 4 != 0)) return false;
     if (segs[s].lda % 4 != 0 || (reinterpret_cast<uintptr_t>(segs[s].A) & 15)) return false;
     ktot += segs[s].K;
   }
@@ -654,8 +663,8 @@ static int tn_grid(int64_t M, int64_t K) {
 
 size_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t Ktot, int transA, int transB) {
   (void)transB;
-  if (N > TC_MAX_N) return 0;
   if (transA) {
+    if (N > TC_MAX_N) return 0;
     if (M > 32 * TC_BM) return 0;
     return align_up((size_t)tn_grid(M, Ktot) * cdiv(M, TC_BM) * TC_BM * N * sizeof(float), 256) + 256;
   }
@@ -732,11 +741,16 @@ int gemm_tc(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t M
   for (int s = 0; s < 4; ++s) {
     const int ss = s < nseg ? s : 0;
     if (int rc = make_map(&maps[s], segs[ss].A, (uint64_t)segs[ss].K, (uint64_t)M, (uint64_t)segs[ss].lda, TC_BM)) return rc;
-    p.kb_seg[s] = s < nseg ? (int)(segs[s].K / TC_BK) : 0;
+    p.kb_seg[s] = s < nseg ? (int)cdiv(segs[s].K, TC_BK) : 0;
   }
-  if (int rc = make_map(&mbhi, bhi, (uint64_t)ktot, (uint64_t)N, (uint64_t)ktot, (uint32_t)N)) return rc;
-  if (int rc = make_map(&mblo, blo, (uint64_t)ktot, (uint64_t)N, (uint64_t)ktot, (uint32_t)N)) return rc;
-  p.kb_total = (int)(ktot / TC_BK);
+  p.m_tiles = (int)cdiv(M, TC_BM);
+  // 256-column chunks keep the B tile traffic per flop lowest; fall back to 128 when 256 would leave SMs without a tile
+  p.n_chunk = (N > 128 && (int64_t)p.m_tiles * cdiv(N, TC_MAX_N) < kSMs) ? 128 : TC_MAX_N;
+  p.n_chunks = (int)cdiv(N, p.n_chunk);
+  p.n_mma = N <= p.n_chunk ? (int)N : p.n_chunk;
+  if (int rc = make_map(&mbhi, bhi, (uint64_t)ktot, (uint64_t)N, (uint64_t)ktot, (uint32_t)p.n_mma)) return rc;
+  if (int rc = make_map(&mblo, blo, (uint64_t)ktot, (uint64_t)N, (uint64_t)ktot, (uint32_t)p.n_mma)) return rc;
+  p.kb_total = (int)cdiv(ktot, TC_BK);
   p.M = (int)M; p.N = (int)N; p.C = C; p.ldc = ldc; p.bias = bias; p.relu = relu; p.accumulate = accumulate;
   p.m_tiles = (int)cdiv(M, TC_BM);
   p.drain_kb = TC_DRAIN_KB;
@@ -747,7 +761,8 @@ int gemm_tc(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t M
     DC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  const int grid = p.m_tiles < kSMs ? p.m_tiles : kSMs;
+  const int64_t tiles = (int64_t)p.m_tiles * p.n_chunks;
+  const int grid = (int)(tiles < kSMs ? tiles : kSMs);
   gemm_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], mbhi, mblo, p);
   DC_LAUNCH_CHECK();
   return DC_OK;

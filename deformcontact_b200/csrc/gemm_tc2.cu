@@ -1,0 +1,532 @@
+// K2 v2 — unified tcgen05 kind::tf32 GEMM with the 3-term error-compensated split ("3xTF32")
+//
+//   C[M,N] = act( sum_s opA(A_s)[M,K_s] opB(B_s)[K_s,N] + bias ) (+C)        fp32 in / out, fp32-class accuracy
+//
+// for every operand layout (A stored [M,K] or [K,M]; B stored [N,K] or [K,N]), any M, N, K.  What changed against
+// gemm_tc.cu (round-1 K2 / K3), and why (profiles/r01_*):
+//   * The tensor core truncates its fp32 TMEM accumulator on every MMA, so an accumulation chain is cut every
+//     `drain_kb` k-blocks.  v1 drained a chain by read-modify-writing the C tile in global memory while the MMA
+//     pipe waited (45 % of the kernel at K = 1024, 60 % at K = 3048).  Here a tile is 128 x 128, the three main
+//     accumulators of TMEM (3 x 128 columns, + 128 for the cross terms) are used round-robin, and the eight
+//     epilogue warps add finished chains into REGISTERS (64 fp32 per thread, round-to-nearest) while the next
+//     chains run: no global traffic, no MMA stall; C is written once.
+//   * Both operands arrive as raw fp32 tiles by TMA and are split into hi / lo in shared memory (v1 loaded
+//     pre-split B_hi and B_lo: 80 KB per k-block, L2-bound at ~207 TFLOP/s; now 32 KB per k-block), so there is
+//     no packing pre-kernel and no workspace for it.
+//   * MN-major operands (transposed A, untransposed B) use the SWIZZLE_128B_BASE32B canonical layout
+//     (TMA: SWIZZLE_128B_ATOM_32B boxes of 32 x 32) found on hardware in round 1 — no explicit transposes.
+//   * Work item = (row tile, column chunk, k part): when M x N alone gives fewer tiles than SMs the contraction
+//     is cut into parts whose partial tiles go to slabs that a second kernel sums in fixed order (deterministic).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace dcb {
+namespace {
+
+constexpr int T2_BM = 128, T2_BN = 128, T2_BK = 32;
+constexpr int T2_STAGES = 3;
+constexpr int T2_THREADS = 512;
+constexpr int T2_TILE_BYTES = T2_BM * T2_BK * 4;              // 16 KB (A and B tiles have the same shape)
+constexpr int T2_STAGE_BYTES = 4 * T2_TILE_BYTES;             // A hi(raw), A lo, B hi(raw), B lo
+constexpr int T2_EPI_ROW = 20;                                // staging row: 16 floats + 4 pad
+constexpr int T2_EPI_WARP_FLOATS = 32 * T2_EPI_ROW;
+constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOATS * 4 + 256 + 1024;
+constexpr int T2_DRAIN_KB = 8;                                // chain length in k-blocks (32 MMA steps)
+constexpr int T2_MAX_KPARTS = 16;
+
+struct T2Params {
+  int nseg;
+  int kb_seg[4];          // k-blocks per segment
+  int kb_total;
+  int M, N;
+  int m_tiles, n_chunks, k_parts, kb_per_part, items;
+  int a_mn, b_mn;         // 1 = operand is MN-major in memory (A stored [K,M] / B stored [K,N])
+  int drain_kb;
+  float* C;
+  long long ldc;
+  const float* bias;
+  int relu, accumulate;
+  float* partial;         // [k_parts, M, N] when k_parts > 1
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile [128 rows x 32 k]: SWIZZLE_128B, 8-row groups 1024 B apart; one K = 8 step = +32 B
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// MN-major operand tile: 4 TMA boxes [32 k-rows x 32 elements] (SWIZZLE_128B_ATOM_32B) 4096 B apart;
+// SWIZZLE_128B_BASE32B canonical layout: LBO = 4096 (next 32 elements along M/N), SBO = 512 (next 4 k-rows);
+// one K = 8 step = +1024 B
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((4096 >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+
+#define T2_TMEM_LD32(R, ADDR)                                                                                            \
+  asm volatile(                                                                                                         \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                         \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, " \
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                                                                 \
+      : "=r"(R[0]), "=r"(R[1]), "=r"(R[2]), "=r"(R[3]), "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7]), "=r"(R[8]),    \
+        "=r"(R[9]), "=r"(R[10]), "=r"(R[11]), "=r"(R[12]), "=r"(R[13]), "=r"(R[14]), "=r"(R[15]), "=r"(R[16]),         \
+        "=r"(R[17]), "=r"(R[18]), "=r"(R[19]), "=r"(R[20]), "=r"(R[21]), "=r"(R[22]), "=r"(R[23]), "=r"(R[24]),        \
+        "=r"(R[25]), "=r"(R[26]), "=r"(R[27]), "=r"(R[28]), "=r"(R[29]), "=r"(R[30]), "=r"(R[31])                       \
+      : "r"(ADDR))
+
+struct T2Item {
+  int m0, n0, part, kb0, kb1;
+};
+__device__ __forceinline__ T2Item t2_item(const T2Params& p, int w) {
+  T2Item it;
+  it.part = w % p.k_parts;
+  const int mn = w / p.k_parts;
+  it.n0 = (mn % p.n_chunks) * T2_BN;
+  it.m0 = (mn / p.n_chunks) * T2_BM;
+  it.kb0 = it.part * p.kb_per_part;
+  it.kb1 = min(p.kb_total, it.kb0 + p.kb_per_part);
+  return it;
+}
+
+__global__ void __launch_bounds__(T2_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
+                const __grid_constant__ CUtensorMap mapB2, const __grid_constant__ CUtensorMap mapB3, const T2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  float* epi_stage = reinterpret_cast<float*>(base_ptr + T2_STAGES * T2_STAGE_BYTES);
+  const uint32_t bar_base = base + T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOATS * 4;
+  // barriers (8 B each): full[3], xform[3], empty[3], tfull[3], tempty[3], cfull, cempty; then the TMEM pointer
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto xform_bar = [&](int s) { return bar_base + 24u + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 48u + 8u * s; };
+  auto tfull_bar = [&](int j) { return bar_base + 72u + 8u * j; };
+  auto tempty_bar = [&](int j) { return bar_base + 96u + 8u * j; };
+  const uint32_t cfull_bar = bar_base + 120u, cempty_bar = bar_base + 128u;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOATS * 4 + 144);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < T2_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(xform_bar(s), 128);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 256);
+    }
+    mbar_init(cfull_bar, 1);
+    mbar_init(cempty_bar, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const CUtensorMap* mA[4] = {&mapA0, &mapA1, &mapA2, &mapA3};
+      const CUtensorMap* mB[4] = {&mapB0, &mapB1, &mapB2, &mapB3};
+      int it = 0;
+      for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
+        const T2Item item = t2_item(p, w);
+        int seg = 0, seg_kb0 = 0;   // segment containing k-block kb, and its first k-block
+        for (int kb = item.kb0; kb < item.kb1; ++kb, ++it) {
+          while (kb >= seg_kb0 + p.kb_seg[seg]) { seg_kb0 += p.kb_seg[seg]; ++seg; }
+          const int k0 = (kb - seg_kb0) * T2_BK;
+          const int st = it % T2_STAGES;
+          const uint32_t ph = (it / T2_STAGES) & 1;
+          mbar_wait(empty_bar(st), ph ^ 1);
+          const uint32_t sbase = base + st * T2_STAGE_BYTES;
+          mbar_expect_tx(full_bar(st), 2 * T2_TILE_BYTES);
+          if (p.a_mn) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_load_2d(sbase + c * 4096, mA[seg], full_bar(st), item.m0 + c * 32, k0);
+          } else {
+            tma_load_2d(sbase, mA[seg], full_bar(st), k0, item.m0);
+          }
+          if (p.b_mn) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_load_2d(sbase + 2 * T2_TILE_BYTES + c * 4096, mB[seg], full_bar(st), item.n0 + c * 32, k0);
+          } else {
+            tma_load_2d(sbase + 2 * T2_TILE_BYTES, mB[seg], full_bar(st), k0, item.n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                             ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
+      const uint32_t a_adv = p.a_mn ? (1024u >> 4) : (32u >> 4), b_adv = p.b_mn ? (1024u >> 4) : (32u >> 4);
+      const uint32_t d_cross = tmem_base;
+      int it = 0, chain = 0, itemc = 0;
+      for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++itemc) {
+        const T2Item item = t2_item(p, w);
+        mbar_wait(cempty_bar, (itemc & 1) ^ 1);
+        tc_fence_after();
+        bool cross_started = false;
+        for (int kc0 = item.kb0; kc0 < item.kb1; kc0 += p.drain_kb, ++chain) {
+          const int kc1 = min(item.kb1, kc0 + p.drain_kb);
+          const int j = chain % 3;
+          const uint32_t d_main = tmem_base + (uint32_t)(T2_BN * (1 + j));
+          mbar_wait(tempty_bar(j), ((chain / 3) & 1) ^ 1);
+          tc_fence_after();
+          for (int kb = kc0; kb < kc1; ++kb, ++it) {
+            const int st = it % T2_STAGES;
+            const uint32_t ph = (it / T2_STAGES) & 1;
+            mbar_wait(full_bar(st), ph);
+            mbar_wait(xform_bar(st), ph);
+            tc_fence_after();
+            const uint32_t sbase = base + st * T2_STAGE_BYTES;
+            const uint64_t a_hi = p.a_mn ? desc_mnmajor(sbase) : desc_kmajor(sbase);
+            const uint64_t a_lo = p.a_mn ? desc_mnmajor(sbase + T2_TILE_BYTES) : desc_kmajor(sbase + T2_TILE_BYTES);
+            const uint64_t b_hi = p.b_mn ? desc_mnmajor(sbase + 2 * T2_TILE_BYTES) : desc_kmajor(sbase + 2 * T2_TILE_BYTES);
+            const uint64_t b_lo = p.b_mn ? desc_mnmajor(sbase + 3 * T2_TILE_BYTES) : desc_kmajor(sbase + 3 * T2_TILE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < T2_BK / 8; ++kk) {
+              const uint64_t aa = (uint64_t)(kk * a_adv), bb = (uint64_t)(kk * b_adv);
+              umma_tf32(d_cross, a_lo + aa, b_hi + bb, idesc, cross_started ? 1u : 0u);   // whole-item chain (tiny values)
+              cross_started = true;
+              umma_tf32(d_cross, a_hi + aa, b_lo + bb, idesc, 1u);
+              umma_tf32(d_main, a_hi + aa, b_hi + bb, idesc, (kb > kc0 || kk > 0) ? 1u : 0u);   // restarted every chain
+            }
+            umma_commit(empty_bar(st));
+          }
+          umma_commit(tfull_bar(j));
+        }
+        umma_commit(cfull_bar);
+      }
+    }
+  } else if (warp >= 8 && warp < 12) {
+    // ------------------------------------------------------------------ split warps: X -> X_hi (in place), X_lo
+    const int t = threadIdx.x - 256;
+    int it = 0;
+    for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
+      const T2Item item = t2_item(p, w);
+      for (int kb = item.kb0; kb < item.kb1; ++kb, ++it) {
+        const int st = it % T2_STAGES;
+        const uint32_t ph = (it / T2_STAGES) & 1;
+        mbar_wait(full_bar(st), ph);
+        uint4* a = reinterpret_cast<uint4*>(base_ptr + st * T2_STAGE_BYTES);
+        uint4* b = reinterpret_cast<uint4*>(base_ptr + st * T2_STAGE_BYTES + 2 * T2_TILE_BYTES);
+        constexpr int LO = T2_TILE_BYTES / 16;   // the lo tile follows its hi tile
+#pragma unroll
+        for (int i = 0; i < 2 * T2_TILE_BYTES / 16 / 128; ++i) {
+          uint4* src = (i & 1) ? b : a;
+          const int idx = t + (i >> 1) * 128;
+          const uint4 v = src[idx];
+          const uint4 h = make_uint4(v.x & 0xFFFFE000u, v.y & 0xFFFFE000u, v.z & 0xFFFFE000u, v.w & 0xFFFFE000u);
+          uint4 l;
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+          src[idx] = h;
+          src[idx + LO] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(xform_bar(st));
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: warps 4-7 columns 0-63, warps 12-15 columns 64-127
+    const int q = warp & 3;               // TMEM lane quarter == warp % 4
+    const int half = warp >= 12 ? 1 : 0;
+    float* stg = epi_stage + ((half * 4) + q) * T2_EPI_WARP_FLOATS;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) && ((p.N & 3) == 0 || p.k_parts == 1);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+    int chain = 0, itemc = 0;
+    for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++itemc) {
+      const T2Item item = t2_item(p, w);
+      float acc[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      for (int kc0 = item.kb0; kc0 < item.kb1; kc0 += p.drain_kb, ++chain) {
+        const int j = chain % 3;
+        mbar_wait(tfull_bar(j), (chain / 3) & 1);
+        tc_fence_after();
+        uint32_t r[32];
+        T2_TMEM_LD32(r, lane_addr + (uint32_t)(T2_BN * (1 + j)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(r[i]);
+        T2_TMEM_LD32(r, lane_addr + (uint32_t)(T2_BN * (1 + j)) + 32u);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(tempty_bar(j));   // the accumulator is free again as soon as it sits in registers
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[32 + i] += __uint_as_float(r[i]);
+      }
+      {
+        mbar_wait(cfull_bar, itemc & 1);
+        tc_fence_after();
+        uint32_t r[32];
+        T2_TMEM_LD32(r, lane_addr);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(r[i]);
+        T2_TMEM_LD32(r, lane_addr + 32u);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(cempty_bar);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[32 + i] += __uint_as_float(r[i]);
+      }
+      // ---- write the 32 x 64 block of this warp, 16 columns at a time through a padded staging tile
+      const bool to_slab = p.k_parts > 1;
+      float* outp = to_slab ? p.partial + (size_t)item.part * (size_t)p.M * p.N : p.C;
+      const long long ldo = to_slab ? (long long)p.N : p.ldc;
+      const bool add_c = !to_slab && p.accumulate;
+      const bool do_relu = !to_slab && p.relu;
+      const float* bias = to_slab ? nullptr : p.bias;
+      const int row0 = item.m0 + q * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int jv = 0; jv < 16; jv += 4)
+          *reinterpret_cast<float4*>(stg + lane * T2_EPI_ROW + jv) = make_float4(acc[g * 16 + jv], acc[g * 16 + jv + 1], acc[g * 16 + jv + 2], acc[g * 16 + jv + 3]);
+        __syncwarp();
+        const int c4 = (lane & 3) * 4;
+        const int col = item.n0 + half * 64 + g * 16 + c4;
+        if (vec_ok && col + 3 < p.N) {
+          const float4 bv = bias ? *reinterpret_cast<const float4*>(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int it4 = 0; it4 < 4; ++it4) {
+            const int rr = it4 * 8 + (lane >> 2);
+            const int row = row0 + rr;
+            if (row < p.M) {
+              float4 v = *reinterpret_cast<const float4*>(stg + rr * T2_EPI_ROW + c4);
+              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              float4* dst = reinterpret_cast<float4*>(outp + (long long)row * ldo + col);
+              if (add_c) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+              if (do_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              *dst = v;
+            }
+          }
+        } else {
+          for (int it4 = 0; it4 < 4; ++it4) {
+            const int rr = it4 * 8 + (lane >> 2);
+            const int row = row0 + rr;
+            for (int e = 0; e < 4; ++e) {
+              if (row < p.M && col + e < p.N) {
+                float v = stg[rr * T2_EPI_ROW + c4 + e] + (bias ? bias[col + e] : 0.f);
+                float* dst = outp + (long long)row * ldo + col + e;
+                if (add_c) v += *dst;
+                if (do_relu) v = fmaxf(v, 0.f);
+                *dst = v;
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// C = act( sum over k parts (fixed order) + bias ) (+C)
+__global__ void t2_reduce_kernel(const float* __restrict__ partial, int parts, long long MN, int N, float* __restrict__ C,
+                                 long long ldc, const float* __restrict__ bias, int relu, int accumulate) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= MN) return;
+  const long long m = idx / N;
+  const int n = (int)(idx % N);
+  float s = 0.f;
+  for (int z = 0; z < parts; ++z) s += partial[(size_t)z * MN + idx];
+  if (bias) s += bias[n];
+  float* dst = C + m * ldc + n;
+  if (accumulate) s += *dst;
+  if (relu) s = fmaxf(s, 0.f);
+  *dst = s;
+}
+
+typedef CUresult (*EncodeFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn2 get_encode2() {
+  static EncodeFn2 fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn2>(sym);
+  }
+  return fn;
+}
+
+// operand stored as `rows` x `inner` fp32 with leading dimension ld; box = [32 inner, box_rows]
+int make_map2(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t rows, uint64_t ld_elems, uint32_t box_rows,
+              CUtensorMapSwizzle swz) {
+  EncodeFn2 enc = get_encode2();
+  DC_REQUIRE(enc, DC_ECUDA, "gemm_tc2: cuTensorMapEncodeTiled not available");
+  cuuint64_t gdim[2] = {inner, rows};
+  cuuint64_t gstr[1] = {ld_elems * 4};
+  cuuint32_t box[2] = {T2_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DC_REQUIRE(r == CUDA_SUCCESS, DC_ECUDA, "gemm_tc2: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return DC_OK;
+}
+
+int t2_k_parts(int64_t M, int64_t N, int64_t kb_total) {
+  const int64_t mn = cdiv(M, T2_BM) * cdiv(N, T2_BN);
+  if (mn >= kSMs) return 1;
+  int64_t parts = kSMs / mn;                          // fill the machine once
+  const int64_t max_parts = kb_total / T2_DRAIN_KB;   // at least one full chain per part
+  if (parts > max_parts) parts = max_parts;
+  if (parts > T2_MAX_KPARTS) parts = T2_MAX_KPARTS;
+  return parts < 1 ? 1 : (int)parts;
+}
+}  // namespace
+
+bool gemm_tc2_supported(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t M, int64_t N) {
+  if (nseg < 1 || nseg > 4 || M < 1 || N < 1 || M >= (1ll << 31) || N >= (1ll << 31)) return false;
+  if (nseg > 1 && (transA || !transB)) return false;   // multi-segment: K-major A and B only (the TAGConv layer GEMM)
+  for (int s = 0; s < nseg; ++s) {
+    if (segs[s].K <= 0 || segs[s].K >= (1ll << 31)) return false;
+    if (segs[s].lda % 4 != 0 || segs[s].ldb % 4 != 0) return false;   // TMA: 16-byte row pitch
+    if ((reinterpret_cast<uintptr_t>(segs[s].A) & 15) || (reinterpret_cast<uintptr_t>(segs[s].B) & 15)) return false;
+  }
+  return true;
+}
+
+size_t gemm_tc2_workspace_bytes(int64_t M, int64_t N, int64_t Ktot) {
+  const int parts = t2_k_parts(M, N, cdiv(Ktot, T2_BK));
+  return parts > 1 ? align_up((size_t)parts * M * N * sizeof(float), 256) + 256 : 0;
+}
+
+int gemm_tc2(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t M, int64_t N, float* C, int64_t ldc,
+             const float* bias, int relu, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  DC_REQUIRE(gemm_tc2_supported(segs, nseg, transA, transB, M, N), DC_ENOSUP, "gemm_tc2: layout not supported by the tcgen05 path");
+  T2Params p{};
+  p.nseg = nseg;
+  p.a_mn = transA ? 1 : 0;
+  p.b_mn = transB ? 0 : 1;
+  CUtensorMap mA[4], mB[4];
+  int64_t ktot = 0;
+  for (int s = 0; s < 4; ++s) {
+    const int ss = s < nseg ? s : 0;
+    const uint64_t K = (uint64_t)segs[ss].K;
+    if (transA) {   // stored [K, M]: inner = M
+      if (int rc = make_map2(&mA[s], segs[ss].A, (uint64_t)M, K, (uint64_t)segs[ss].lda, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+    } else {        // stored [M, K]: inner = K
+      if (int rc = make_map2(&mA[s], segs[ss].A, K, (uint64_t)M, (uint64_t)segs[ss].lda, T2_BM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    }
+    if (transB) {   // stored [N, K]: inner = K
+      if (int rc = make_map2(&mB[s], segs[ss].B, K, (uint64_t)N, (uint64_t)segs[ss].ldb, T2_BN, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    } else {        // stored [K, N]: inner = N
+      if (int rc = make_map2(&mB[s], segs[ss].B, (uint64_t)N, K, (uint64_t)segs[ss].ldb, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+    }
+    p.kb_seg[s] = s < nseg ? (int)cdiv(segs[s].K, T2_BK) : (1 << 30);
+    if (s < nseg) ktot += cdiv(segs[s].K, T2_BK);
+  }
+  p.kb_total = (int)ktot;
+  p.M = (int)M; p.N = (int)N;
+  p.m_tiles = (int)cdiv(M, T2_BM);
+  p.n_chunks = (int)cdiv(N, T2_BN);
+  p.k_parts = t2_k_parts(M, N, p.kb_total);
+  p.kb_per_part = (int)(cdiv(cdiv(p.kb_total, p.k_parts), T2_DRAIN_KB) * T2_DRAIN_KB);   // whole chains per part
+  p.k_parts = (int)cdiv(p.kb_total, p.kb_per_part);
+  p.items = p.m_tiles * p.n_chunks * p.k_parts;
+  p.drain_kb = T2_DRAIN_KB;
+  if (const char* e = getenv("DCB200_DRAIN_KB")) p.drain_kb = atoi(e) > 0 ? atoi(e) : T2_DRAIN_KB;
+  p.C = C; p.ldc = ldc; p.bias = bias; p.relu = relu; p.accumulate = accumulate;
+  if (p.k_parts > 1) {
+    const size_t need = align_up((size_t)p.k_parts * M * N * sizeof(float), 256) + 256;
+    DC_REQUIRE(workspace && workspace_bytes >= need, DC_EWORKSPACE, "gemm_tc2: workspace %zu < %zu", workspace_bytes, need);
+    p.partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    DC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = p.items < kSMs ? p.items : kSMs;
+  gemm_tc2_kernel<<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(mA[0], mA[1], mA[2], mA[3], mB[0], mB[1], mB[2], mB[3], p);
+  DC_LAUNCH_CHECK();
+  if (p.k_parts > 1) {
+    const long long MN = (long long)M * N;
+    t2_reduce_kernel<<<(unsigned)cdiv(MN, 256), 256, 0, st>>>(p.partial, p.k_parts, MN, (int)N, C, ldc, bias, relu, accumulate);
+    DC_LAUNCH_CHECK();
+  }
+  return DC_OK;
+}
+
+}  // namespace dcb

@@ -3,8 +3,8 @@
 Mirrors models/model.py:23-97 (constructor arguments, module names — hence state-dict keys —
 forward order) and models/model_loader.py:3-16.  The encoder loops (models/model.py:69-78) —
 the hot path — run in libdcb200 with bias+ReLU fused into the layer epilogue; the cross
-attention (models/model.py:7-21,82) and decoder MLP (:52-64,88) are *outside* the hot-path scope
- and stay plain fp32 torch/cuBLAS here.
+attention (models/model.py:7-21,82) runs on the same tcgen05 3xTF32 GEMMs
+(attention.py); the decoder MLP (:52-64,88) stays plain fp32 torch/cuBLAS.
 
 ``attn_group``: the reference attention is unmasked over the whole batch (a soft node attends
 to the collider nodes of *every* sample, models/model.py:16-18).  ``attn_group=None``
@@ -17,7 +17,12 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import layers
+import os
+
+from . import attention, layers
+
+# "dcb200": the cross attention runs on libdcb200 (attention.py); "torch": plain fp32 torch / cuBLAS (round-1 path)
+ATTENTION_IMPL = os.environ.get("DCB200_ATTENTION", "dcb200")
 
 EVERYDAY = dict(input_dims=[21, 25], hidden_dim=256, output_dim=3, encoder_layers=2, decoder_layers=3,
                 dropout_rate=0.0, knn_k=7, backbone="TAGConv", use_mha=True, num_mha_heads=2,
@@ -100,6 +105,11 @@ class GraphNet(nn.Module):
 
     def attend(self, x_resting, x_rigid, graph_resting, graph_rigid):
         G = self.attn_group
+        if ATTENTION_IMPL == "dcb200":   # N1: tcgen05 3xTF32 GEMMs + fused softmax kernels (attention.py)
+            has_ptr = getattr(graph_resting, "ptr", None) is not None and getattr(graph_rigid, "ptr", None) is not None
+            ps = _host_ptr(graph_resting) if has_ptr else [0, x_resting.shape[0]]
+            pr = _host_ptr(graph_rigid) if has_ptr else [0, x_rigid.shape[0]]
+            return attention.cross_attention(x_resting, x_rigid, self.multihead_attention.attention_heads, ps, pr, G)
         if G is None:
             return self.multihead_attention(x_resting, x_rigid)
         ps, pr = _host_ptr(graph_resting), _host_ptr(graph_rigid)

@@ -183,6 +183,12 @@ DC_API size_t dc_colsum_workspace_bytes(int64_t M, int64_t N);
 DC_API int dc_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* workspace,
               size_t workspace_bytes, dc_stream_t stream);
 
+/* N1 — element-wise pieces of the dense cross attention (models/model.py:7-21; the matrix products
+ * run through dc_gemm): in-place row softmax  S[m,:] <- softmax(S[m,:])  and its backward, in place on dP:
+ * dS[m,n] = P[m,n] * (dP[m,n] - sum_j dP[m,j] P[m,j]).  One CTA per row, fixed reduction tree (deterministic). */
+DC_API int dc_softmax_rows(float* S, int64_t ld, int64_t M, int64_t N, dc_stream_t stream);
+DC_API int dc_softmax_bwd_rows(const float* P, int64_t ldp, float* dP, int64_t ldd, int64_t M, int64_t N, dc_stream_t stream);
+
 /* dX = dY * (Y > 0)  (backward of the ReLU fused into dc_gemm's epilogue; models/model.py:71,77) */
 DC_API int dc_relu_bwd(const float* Y, const float* dY, float* dX, int64_t numel, dc_stream_t stream);
 

@@ -1,3 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for n in 1000 1500 1750 2000 2500; do echo "== nodes $n"; timeout 300 python scripts/k1_lab.py --nodes $n --graphs $((512000/n)) --variants lean,blocks:4,blocks:28 2>&1 | tail -3; done
+timeout 900 python -m pytest tests/test_gpu_attention.py tests/test_gpu_kernels.py tests/test_gpu_layers.py -m gpu -q -x -k "attention or gemm or layer or graphnet or softmax" 2>&1 | tail -15
+timeout 300 python scripts/attn_lab.py 4 2>&1 | tail -12

@@ -1,0 +1,86 @@
+"""N1: the dense cross attention (models/model.py:7-21) on libdcb200 — forward and hand-derived backward against
+the reference formula in fp32 and, where the unscaled softmax makes fp32 itself ill-conditioned, the fp64 arbiter."""
+import pytest
+import torch
+
+from helpers import assert_close, assert_close_arbiter
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dc():
+    import deformcontact_b200 as d
+    return d
+
+
+def _ref(xs, xr, W, b, groups):
+    """models/model.py:14-19 applied per attention group."""
+    outs = []
+    for s0, s1, r0, r1 in groups:
+        q, k = xs[s0:s1] @ W.T + b, xr[r0:r1] @ W.T + b
+        outs.append(torch.softmax(q @ k.T, dim=-1) @ xr[r0:r1])
+    return torch.cat(outs, 0)
+
+
+@pytest.mark.parametrize("F,ptr_s,ptr_r,group", [
+    (64, [0, 300, 700, 1000, 1500], [0, 40, 100, 180, 240], 2),       # ragged groups
+    (256, [0, 2000, 4000], [0, 764, 1528], None),                      # whole batch, N-chunked scores (1528 > 256)
+    (32, [0, 130, 131, 400], [0, 36, 40, 72], 1),                      # tiny groups (SIMT fallback below the size cut)
+    (128, [0, 1000, 2000], [0, 381, 763], 1),                          # nr % 4 != 0 in one group (fallback layout path)
+])
+def test_cross_attention_forward_backward(dc, F, ptr_s, ptr_r, group):
+    from deformcontact_b200 import attention
+    g = torch.Generator().manual_seed(F)
+    Ns, Nr = ptr_s[-1], ptr_r[-1]
+    xs = torch.randn(Ns, F, generator=g).relu()            # encoder outputs are post-ReLU
+    xr = torch.randn(Nr, F, generator=g).relu()
+    W = (torch.rand(F, F, generator=g) * 2 - 1) / F ** 0.5 * 0.5
+    b = (torch.rand(F, generator=g) * 2 - 1) / F ** 0.5
+    go = torch.randn(Ns, F, generator=g)
+    groups = attention._groups(ptr_s, ptr_r, group)
+
+    def run(dtype, dev):
+        t = [v.detach().clone().to(dtype=dtype, device=dev).requires_grad_(True) for v in (xs, xr, W, b)]
+        if dev == "cuda":
+            out = attention._AttnHeadFn.apply(*t, groups)
+        else:
+            out = _ref(*t, groups)
+        out.backward(go.to(dtype=dtype, device=dev))
+        return [out] + [v.grad for v in t]
+
+    ours, r32, r64 = run(torch.float32, "cuda"), run(torch.float32, "cpu"), run(torch.float64, "cpu")
+    for name, a, b32, b64 in zip(("out", "dxs", "dxr", "dW", "db"), ours, r32, r64):
+        assert_close_arbiter(a, b32, b64, what=f"attention {name} F={F}")
+
+
+def test_softmax_rows_kernels(dc):
+    from deformcontact_b200 import attention
+    g = torch.Generator().manual_seed(0)
+    for M, N in [(37, 1), (64, 3048), (5, 5000), (300, 257)]:
+        S = (torch.randn(M, N, generator=g) * 8).cuda()
+        ref = torch.softmax(S.double(), -1)
+        P = attention.softmax_rows_(S.clone())
+        assert_close(P, ref.float(), what=f"softmax {M}x{N}")
+        dP = torch.randn(M, N, generator=g).cuda()
+        ref_d = ref * (dP.double() - (dP.double() * ref).sum(-1, keepdim=True))
+        dS = attention.softmax_bwd_rows_(ref.float().contiguous(), dP.clone())
+        assert_close(dS, ref_d.float(), tol=2e-5, what=f"softmax bwd {M}x{N}")
+        # strided views (padded rows)
+        buf = torch.zeros(M, N + 3).cuda()
+        buf[:, :N] = S
+        assert torch.equal(attention.softmax_rows_(buf[:, :N]), P)
+
+
+def test_gemm_tc_wide_n_and_ragged_k(dc):
+    """K2 with N > 256 (column chunks) and K % 32 != 0 (TMA zero fill) against fp64."""
+    from deformcontact_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    for M, N, K, tb in [(1000, 3048, 256, True), (777, 600, 3048, False), (300, 257 * 4, 100, True), (2000, 256, 3048, False)]:
+        A = torch.randn(M, K, generator=g).cuda()
+        B = (torch.randn(N, K, generator=g) if tb else torch.randn(K, N, generator=g)).cuda()
+        ref = A.double() @ (B.double().T if tb else B.double())
+        out = ops.gemm([(A, B)], M, N, trans_b=tb, precision=dc._abi.GEMM_TF32X3)
+        assert_close(out, ref.float(), what=f"gemm_tc {M}x{N}x{K}")
+        out2 = ops.gemm([(A, B)], M, N, trans_b=tb, precision=dc._abi.GEMM_FP32)
+        assert_close(out2, ref.float(), what=f"gemm_simt {M}x{N}x{K}")
