@@ -101,9 +101,10 @@ class _AttnHeadFn(torch.autograd.Function):
 ATTN_TN_PRECISION = _abi.GEMM_PREFER_TC
 
 
-def cross_attention(x_resting, x_rigid, heads, ptr_s, ptr_r, group=None):
+def cross_attention(x_resting, x_rigid, heads, ptr_s, ptr_r, group=None, concat=True):
     """``heads``: iterable of ``nn.Linear``; returns the head outputs concatenated along the feature axis
-    (models/model.py:14-21).  ``ptr_s`` / ``ptr_r``: host lists of graph offsets of the two batches."""
+    (models/model.py:14-21), or as a list when ``concat`` is False (the decoder consumes them as GEMM K-segments).
+    ``ptr_s`` / ``ptr_r``: host lists of graph offsets of the two batches."""
     groups = _groups(ptr_s, ptr_r, group)
     outs = [_AttnHeadFn.apply(x_resting, x_rigid, h.weight, h.bias, groups) for h in heads]
-    return torch.cat(outs, dim=-1)
+    return torch.cat(outs, dim=-1) if concat else outs

@@ -50,12 +50,16 @@ extern "C" int dc_gemm(const dc_gemm_seg* segs, int nseg, int transA, int transB
       DC_REQUIRE(ok, DC_ENOSUP, "gemm: shape/layout not supported by the tcgen05 path");
       return dcb::gemm_tc2(segs, nseg, transA, transB, M, N, C, ldc, bias, relu, accumulate, workspace, workspace_bytes, st);
     }
-    // AUTO keeps weight-gradient shaped products (transposed A) and small problems on the exact fp32 FFMA kernel
+    // AUTO keeps small problems on the exact fp32 FFMA kernel; DCB200_DW_FP32=1 also keeps weight-gradient shaped
+    // products (transposed A) there, as round 1 did (v1's long truncating accumulation chains cost accuracy; v2 cuts
+    // every chain at 256 contraction elements and sums the chains in fp32 round-to-nearest)
     double work = (double)M * (double)N;
     int64_t ktot = 0;
     for (int s = 0; s < nseg; ++s) ktot += segs[s].K;
     work *= (double)ktot;
-    if (ok && (precision == DC_GEMM_PREFER_TC || (!transA && work >= 1.0e8)))
+    static int dw_fp32 = -1;
+    if (dw_fp32 < 0) { const char* e = getenv("DCB200_DW_FP32"); dw_fp32 = (e && e[0] == '1') ? 1 : 0; }
+    if (ok && (precision == DC_GEMM_PREFER_TC || ((!transA || !dw_fp32) && work >= 1.0e8)))
       return dcb::gemm_tc2(segs, nseg, transA, transB, M, N, C, ldc, bias, relu, accumulate, workspace, workspace_bytes, st);
     return dcb::gemm_simt(segs, nseg, transA, transB, M, N, C, ldc, bias, relu, accumulate, workspace, workspace_bytes, st);
   }

@@ -19,10 +19,12 @@ import torch.nn.functional as F
 
 import os
 
-from . import attention, layers
+from . import attention, layers, mlp
 
 # "dcb200": the cross attention runs on libdcb200 (attention.py); "torch": plain fp32 torch / cuBLAS (round-1 path)
 ATTENTION_IMPL = os.environ.get("DCB200_ATTENTION", "dcb200")
+# same switch for the decoder MLP (mlp.py)
+DECODER_IMPL = os.environ.get("DCB200_DECODER", "dcb200")
 
 EVERYDAY = dict(input_dims=[21, 25], hidden_dim=256, output_dim=3, encoder_layers=2, decoder_layers=3,
                 dropout_rate=0.0, knn_k=7, backbone="TAGConv", use_mha=True, num_mha_heads=2,
@@ -109,7 +111,8 @@ class GraphNet(nn.Module):
             has_ptr = getattr(graph_resting, "ptr", None) is not None and getattr(graph_rigid, "ptr", None) is not None
             ps = _host_ptr(graph_resting) if has_ptr else [0, x_resting.shape[0]]
             pr = _host_ptr(graph_rigid) if has_ptr else [0, x_rigid.shape[0]]
-            return attention.cross_attention(x_resting, x_rigid, self.multihead_attention.attention_heads, ps, pr, G)
+            return attention.cross_attention(x_resting, x_rigid, self.multihead_attention.attention_heads, ps, pr, G,
+                                             concat=DECODER_IMPL != "dcb200")
         if G is None:
             return self.multihead_attention(x_resting, x_rigid)
         ps, pr = _host_ptr(graph_resting), _host_ptr(graph_rigid)
@@ -123,10 +126,28 @@ class GraphNet(nn.Module):
             return out.reshape(x_resting.shape[0], -1)
         return torch.cat([self.multihead_attention(x_resting[ps[a]:ps[b]], x_rigid[pr[a]:pr[b]]) for a, b in bounds], 0)
 
+    def decode(self, segs):
+        """models/model.py:52-64 (Linear, ReLU, Dropout)* + Linear, on dc_gemm with bias + ReLU fused (mlp.py)."""
+        mods = list(self.decoder)
+        x, i = None, 0
+        while i < len(mods):
+            lin = mods[i]
+            relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+            x = mlp.linear(segs if x is None else [x], lin.weight, lin.bias, relu)
+            i += 2 if relu else 1
+            if i < len(mods) and isinstance(mods[i], nn.Dropout):
+                if mods[i].p > 0:
+                    x = F.dropout(x, p=mods[i].p, training=self.training)
+                i += 1
+        return x
+
     def forward(self, graph_resting, graph_rigid):
         x_resting, x_rigid = self.encode(graph_resting, graph_rigid)
         pooled = self.attend(x_resting, x_rigid, graph_resting, graph_rigid)
-        x_out = self.decoder(torch.cat([x_resting, pooled], dim=-1))
+        if DECODER_IMPL == "dcb200":   # the concatenation of models/model.py:84 becomes K-segments of the first GEMM
+            x_out = self.decode([x_resting] + (list(pooled) if isinstance(pooled, (list, tuple)) else [pooled]))
+        else:
+            x_out = self.decoder(torch.cat([x_resting, pooled], dim=-1))
         deformed = graph_resting.clone()
         if self.mode == "res":
             deformed.pos = deformed.pos + x_out  # models/model.py:93 (out-of-place: keeps autograd simple)

@@ -1,4 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_attention.py tests/test_gpu_kernels.py tests/test_gpu_layers.py -m gpu -q -x -k "attention or gemm or layer or graphnet or softmax" 2>&1 | tail -15
-timeout 300 python scripts/attn_lab.py 4 2>&1 | tail -12
+timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.txt
+timeout 600 python bench.py --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_default.json
+python -c "
+import json
+d=json.load(open('gpurun_out/bench_default.json')); print(d['metric'], round(d['value'],2), d.get('e2e') and round(d['e2e']['value'],1), d.get('gpu_launches'), round(d['ms_per_step'],2))
+"
+python scripts/step_profile.py 2>&1 | tail -22

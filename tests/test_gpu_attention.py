@@ -84,3 +84,29 @@ def test_gemm_tc_wide_n_and_ragged_k(dc):
         assert_close(out, ref.float(), what=f"gemm_tc {M}x{N}x{K}")
         out2 = ops.gemm([(A, B)], M, N, trans_b=tb, precision=dc._abi.GEMM_FP32)
         assert_close(out2, ref.float(), what=f"gemm_simt {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("widths,N,relu", [((256, 256, 256), 256, True), ((64,), 3, False), ((32, 96), 40, True), ((21,), 16, False)])
+def test_mlp_linear_segments(dc, widths, N, relu):
+    """mlp.linear == act(cat(segs) @ W.T + b), forward and backward, without the concatenation."""
+    from deformcontact_b200 import mlp
+    g = torch.Generator().manual_seed(N)
+    M = 1500
+    segs = [torch.randn(M, w, generator=g) for w in widths]
+    W = torch.randn(N, sum(widths), generator=g) / sum(widths) ** 0.5
+    b = torch.randn(N, generator=g)
+    go = torch.randn(M, N, generator=g)
+
+    def run(dtype, dev):
+        t = [v.detach().clone().to(dtype=dtype, device=dev).requires_grad_(True) for v in [W, b] + segs]
+        if dev == "cuda":
+            y = mlp.linear(t[2:], t[0], t[1], relu)
+        else:
+            y = torch.cat(t[2:], 1) @ t[0].T + t[1]
+            y = y.relu() if relu else y
+        y.backward(go.to(dtype=dtype, device=dev))
+        return [y] + [v.grad for v in t]
+
+    ours, r32, r64 = run(torch.float32, "cuda"), run(torch.float32, "cpu"), run(torch.float64, "cpu")
+    for i, (a, b32, b64) in enumerate(zip(ours, r32, r64)):
+        assert_close_arbiter(a, b32, b64, what=f"linear tensor {i}")
