@@ -1,5 +1,5 @@
 // dc_gemm — C-ABI entry for the layer GEMMs; dispatches between the exact-fp32 SIMT kernel
-// (gemm_simt.cu) and the tcgen05 3xTF32 tensor-core kernel (gemm_tc.cu).
+// (gemm_simt.cu) and the tcgen05 3xTF32 tensor-core kernel (gemm_tc2.cu).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -8,31 +8,18 @@ namespace dcb {
 size_t gemm_simt_workspace_bytes(int64_t M, int64_t N, int64_t Ktot);
 int gemm_simt(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t M, int64_t N, float* C, int64_t ldc,
               const float* bias, int relu, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t st);
-bool gemm_tc_supported(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t M, int64_t N, const float* C,
-                       int64_t ldc, int accumulate, bool for_auto);
-size_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t Ktot, int transA, int transB);
-int gemm_tc(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t M, int64_t N, float* C, int64_t ldc,
-            const float* bias, int relu, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t st);
 bool gemm_tc2_supported(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t M, int64_t N);
 size_t gemm_tc2_workspace_bytes(int64_t M, int64_t N, int64_t Ktot);
 int gemm_tc2(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t M, int64_t N, float* C, int64_t ldc,
              const float* bias, int relu, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t st);
 }  // namespace dcb
 
-// DCB200_TC=1 selects the round-1 tensor-core kernels (gemm_tc.cu); default is the unified v2 kernel (gemm_tc2.cu)
-static bool use_tc_v1() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DCB200_TC"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
-
 extern "C" size_t dc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K_total, int transA, int transB) {
+  (void)transA; (void)transB;
   if (M < 0 || N < 0 || K_total < 0) return 0;
-  size_t a = dcb::gemm_simt_workspace_bytes(M, N, K_total);
-  size_t b = dcb::gemm_tc_workspace_bytes(M, N, K_total, transA, transB);
-  size_t c = dcb::gemm_tc2_workspace_bytes(M, N, K_total);
-  if (b > a) a = b;
-  return a > c ? a : c;
+  const size_t a = dcb::gemm_simt_workspace_bytes(M, N, K_total);
+  const size_t b = dcb::gemm_tc2_workspace_bytes(M, N, K_total);
+  return a > b ? a : b;
 }
 
 extern "C" int dc_gemm(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t M, int64_t N, float* C,
@@ -44,7 +31,7 @@ extern "C" int dc_gemm(const dc_gemm_seg* segs, int nseg, int transA, int transB
   if (M == 0 || N == 0) return DC_OK;
   DC_REQUIRE(C && ldc >= N, DC_EINVAL, "gemm: bad C / ldc");
   DC_REQUIRE(precision >= DC_GEMM_AUTO && precision <= DC_GEMM_PREFER_TC, DC_EINVAL, "gemm: unknown precision %d", precision);
-  if (!use_tc_v1() && precision != DC_GEMM_FP32) {
+  if (precision != DC_GEMM_FP32) {
     const bool ok = dcb::gemm_tc2_supported(segs, nseg, transA, transB, M, N);
     if (precision == DC_GEMM_TF32X3) {
       DC_REQUIRE(ok, DC_ENOSUP, "gemm: shape/layout not supported by the tcgen05 path");
@@ -61,15 +48,6 @@ extern "C" int dc_gemm(const dc_gemm_seg* segs, int nseg, int transA, int transB
     if (dw_fp32 < 0) { const char* e = getenv("DCB200_DW_FP32"); dw_fp32 = (e && e[0] == '1') ? 1 : 0; }
     if (ok && (precision == DC_GEMM_PREFER_TC || ((!transA || !dw_fp32) && work >= 1.0e8)))
       return dcb::gemm_tc2(segs, nseg, transA, transB, M, N, C, ldc, bias, relu, accumulate, workspace, workspace_bytes, st);
-    return dcb::gemm_simt(segs, nseg, transA, transB, M, N, C, ldc, bias, relu, accumulate, workspace, workspace_bytes, st);
   }
-  if (precision == DC_GEMM_TF32X3) {
-    bool tc_ok = dcb::gemm_tc_supported(segs, nseg, transA, transB, M, N, C, ldc, accumulate, false);
-    DC_REQUIRE(tc_ok, DC_ENOSUP, "gemm: shape/layout not supported by the tcgen05 path");
-    return dcb::gemm_tc(segs, nseg, transA, transB, M, N, C, ldc, bias, relu, accumulate, workspace, workspace_bytes, st);
-  }
-  if ((precision == DC_GEMM_AUTO || precision == DC_GEMM_PREFER_TC) &&
-      dcb::gemm_tc_supported(segs, nseg, transA, transB, M, N, C, ldc, accumulate, precision == DC_GEMM_AUTO))
-    return dcb::gemm_tc(segs, nseg, transA, transB, M, N, C, ldc, bias, relu, accumulate, workspace, workspace_bytes, st);
   return dcb::gemm_simt(segs, nseg, transA, transB, M, N, C, ldc, bias, relu, accumulate, workspace, workspace_bytes, st);
 }

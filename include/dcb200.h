@@ -152,18 +152,20 @@ DC_API int dc_spmm_blocks(const void* slots, const void* recs, const int32_t* ro
 DC_API int dc_edge_relu(const int32_t* rowptr, const int32_t* nbr, const float* p, const float* q, const float* r,
                         float* out, int64_t ld, int64_t num_nodes, int32_t F, int mode, dc_stream_t stream);
 
-/* ---------------------------------------------------------------- K2/K3: layer GEMMs
- * Replaces the Linear calls inside the PyG convs (nn/dense/linear.py; A3c in SURVEY.md).
+/* ---------------------------------------------------------------- K2: dense GEMMs
+ * Replaces the Linear calls inside the PyG convs (nn/dense/linear.py; A3c in SURVEY.md) and, since round 1 late,
+ * carries the matrix products of the cross attention and of the decoder MLP (models/model.py:7-21, 52-64).
  * C[M,N] = act( sum_{s<nseg} opA(A_s)[M,K_s] * opB(B_s)[K_s,N] + bias[N] )  (+ C if accumulate)
  *   transA = 0 : A_s stored [M, K_s] row-major (lda_s);  1 : stored [K_s, M] row-major
  *   transB = 0 : B_s stored [K_s, N] row-major (ldb_s);  1 : stored [N, K_s] row-major
  *   relu = 1 applies max(0, .) in the epilogue; bias may be NULL.
- * precision: DC_GEMM_FP32 = fp32 FFMA (SIMT); DC_GEMM_TF32X3 = tcgen05 kind::tf32 with 3-term
- * error-compensated split (fp32-class accuracy), only for transA=0, transB=1 shapes the tensor
- * path supports (otherwise DC_ENOSUP); DC_GEMM_AUTO picks by size; DC_GEMM_PREFER_TC uses the
- * tensor path whenever the layout allows, regardless of size, else fp32.
- * Split-K (reduction over very long K, e.g. weight gradients over all nodes) uses `workspace`
- * with a fixed-order second-stage sum.
+ * precision: DC_GEMM_FP32 = fp32 FFMA (SIMT, any shape / stride); DC_GEMM_TF32X3 = tcgen05 kind::tf32 with the
+ * 3-term error-compensated split and fp32 round-to-nearest chain sums (fp32-class accuracy, ~1e-6 against fp64) —
+ * every layout for nseg = 1, transA = 0 / transB = 1 for nseg > 1, any M, N, K; needs lda/ldb % 4 == 0 and 16-byte
+ * aligned operands (DC_ENOSUP otherwise); DC_GEMM_AUTO = tensor path for M*N*K >= 1e8 where supported, else fp32;
+ * DC_GEMM_PREFER_TC = tensor path whenever supported, regardless of size.
+ * When M x N alone gives fewer 128 x 128 tiles than SMs the contraction is cut into parts whose partial tiles go to
+ * `workspace` and are summed in fixed order by a second kernel (deterministic).
  */
 enum { DC_GEMM_AUTO = 0, DC_GEMM_FP32 = 1, DC_GEMM_TF32X3 = 2, DC_GEMM_PREFER_TC = 3 };
 typedef struct {
