@@ -33,6 +33,13 @@ import torch.distributed as tdist  # noqa: E402
 METRIC = "train_step_graphs_per_sec"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one K1 hop launch from the ncu --set full capture, relative to the
+# algorithmic bytes of that launch (1040.28 MB measured vs 1069.8 MB algorithmic: edge records partly served by L2)
+K1_NCU_TRAFFIC_RATIO = 1040.28 / 1069.80
+K1_NCU_TRAFFIC_SOURCE = ("profiles/r01_ncu_spmm_v6_lean.csv (C5 hop, N=512000, E=4096000, F=256): 560.5 MB read + 479.8 MB written "
+                         "per launch, scaled by this launch's algorithmic bytes")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -145,7 +152,7 @@ def config_dict(args, world):
             "graphs_per_gpu": args.graphs_per_gpu, "global_batch": args.graphs_per_gpu * world, "nodes_per_graph": args.nodes,
             "knn_k": args.k, "parallelism": f"dp{world}",
             "attention": f"reference unmasked attention applied within groups of {args.attn_group} graphs "
-                         f"(= reference mini-batch of {args.attn_group}, configs/everyday.json:26), fp32 cuBLAS (outside hot-path scope)",
+                         f"(= reference mini-batch of {args.attn_group}, configs/everyday.json:26), on libdcb200: tcgen05 3xTF32 GEMMs (fp32-class accuracy) + fused softmax kernels",
             "l2": "inputs larger than L2 (per-step working set > 1 GB vs 126 MB L2); no explicit flush",
             "structure_build": "CSR pair rebuilt every step (inside the timed region)"}
 
@@ -171,7 +178,7 @@ def run_ours(args):
 
     rank, local, world = ddist.init()
     dev = torch.device("cuda", local)
-    torch.backends.cuda.matmul.allow_tf32 = False   # the torch-side attention/decoder stay true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False   # whatever still runs in torch stays true fp32
     torch.backends.cudnn.allow_tf32 = False
     Bg = args.graphs_per_gpu
     rest, rigid, deformed = synthetic.make_batch(Bg, args.nodes, args.k, first=rank * Bg, device=dev)
@@ -254,7 +261,8 @@ def run_ours(args):
         ach = hop_bytes / (hop_ms * 1e-3) / 1e9
         roofline = {"kernel": f"K1 gather/segmented-sum hop, F=256 ({ops.K1_VARIANT} variant)", "bound": "hbm",
                     "achieved": ach, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": None, "launches": hop_n // args.steps, "avg_launch_ms": hop_ms / hop_n,
+                    "traffic": K1_NCU_TRAFFIC_RATIO * hop_bytes / hop_n, "traffic_source": K1_NCU_TRAFFIC_SOURCE,
+                    "launches": hop_n // args.steps, "avg_launch_ms": hop_ms / hop_n,
                     "algorithmic_bytes_per_launch": hop_bytes / hop_n,
                     "share_of_step": hop_ms / total_ms,
                     "note": "bytes = 8NF+4E+8N+4 per hop (+4NF when a fused addend is read); timed with CUDA events "
@@ -378,7 +386,8 @@ def run_layer(args):
             "edge_traversals_per_sec_fwd_bwd": 6 * E / (fb_ms * 1e-3),
             "hop": {"fwd_ms": hop_ms, "transpose_ms": hop_t_ms, "generic_v1_ms": hop_v1_ms, "edges_per_sec": E / (hop_ms * 1e-3)},
             "roofline": {"kernel": f"K1 hop ({ops.K1_VARIANT})", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": peak_src,
-                         "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": hop_bytes}}
+                         "unit": "GB/s", "frac": ach / hbm_peak, "traffic": K1_NCU_TRAFFIC_RATIO * hop_bytes,
+                         "traffic_source": K1_NCU_TRAFFIC_SOURCE, "algorithmic_bytes_per_launch": hop_bytes}}
     print(json.dumps(line), flush=True)
 
 
