@@ -6,10 +6,10 @@
 // gemm_tc.cu (round-1 K2 / K3), and why (profiles/r01_*):
 //   * The tensor core truncates its fp32 TMEM accumulator on every MMA, so an accumulation chain is cut every
 //     `drain_kb` k-blocks.  v1 drained a chain by read-modify-writing the C tile in global memory while the MMA
-//     pipe waited (45 % of the kernel at K = 1024, 60 % at K = 3048).  Here a tile is 128 x 128, the three main
-//     accumulators of TMEM (3 x 128 columns, + 128 for the cross terms) are used round-robin, and the eight
-//     epilogue warps add finished chains into REGISTERS (64 fp32 per thread, round-to-nearest) while the next
-//     chains run: no global traffic, no MMA stall; C is written once.
+//     pipe waited (45 % of the kernel at K = 1024, 60 % at K = 3048).  Here a tile is 128 x 128, TMEM holds two
+//     main accumulators (alternating per chain) and two cross-term accumulators (alternating per work item), and
+//     the eight epilogue warps add finished chains into REGISTERS (64 fp32 per thread, round-to-nearest) while the
+//     next chain / the next item runs: no global traffic, no MMA stall; C is written once.
 //   * Both operands arrive as raw fp32 tiles by TMA and are split into hi / lo in shared memory (v1 loaded
 //     pre-split B_hi and B_lo: 80 KB per k-block, L2-bound at ~207 TFLOP/s; now 32 KB per k-block), so there is
 //     no packing pre-kernel and no workspace for it.
@@ -154,13 +154,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   float* epi_stage = reinterpret_cast<float*>(base_ptr + T2_STAGES * T2_STAGE_BYTES);
   const uint32_t bar_base = base + T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOATS * 4;
-  // barriers (8 B each): full[3], xform[3], empty[3], tfull[3], tempty[3], cfull, cempty; then the TMEM pointer
+  // barriers (8 B each): full[3], xform[3], empty[3], tfull[2], tempty[2], cfull[2], cempty[2]; then the TMEM pointer
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto xform_bar = [&](int s) { return bar_base + 24u + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 48u + 8u * s; };
   auto tfull_bar = [&](int j) { return bar_base + 72u + 8u * j; };
-  auto tempty_bar = [&](int j) { return bar_base + 96u + 8u * j; };
-  const uint32_t cfull_bar = bar_base + 120u, cempty_bar = bar_base + 128u;
+  auto tempty_bar = [&](int j) { return bar_base + 88u + 8u * j; };
+  auto cfull_bar = [&](int c) { return bar_base + 104u + 8u * c; };
+  auto cempty_bar = [&](int c) { return bar_base + 120u + 8u * c; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOATS * 4 + 144);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -170,11 +171,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       mbar_init(full_bar(s), 1);
       mbar_init(xform_bar(s), 128);
       mbar_init(empty_bar(s), 1);
-      mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 256);
     }
-    mbar_init(cfull_bar, 1);
-    mbar_init(cempty_bar, 256);
+    for (int j = 0; j < 2; ++j) {
+      mbar_init(tfull_bar(j), 1);
+      mbar_init(tempty_bar(j), 256);
+      mbar_init(cfull_bar(j), 1);
+      mbar_init(cempty_bar(j), 256);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -226,18 +229,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                              ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
       const uint32_t a_adv = p.a_mn ? (1024u >> 4) : (32u >> 4), b_adv = p.b_mn ? (1024u >> 4) : (32u >> 4);
-      const uint32_t d_cross = tmem_base;
       int it = 0, chain = 0, itemc = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++itemc) {
         const T2Item item = t2_item(p, w);
-        mbar_wait(cempty_bar, (itemc & 1) ^ 1);
+        const int cx = itemc & 1;   // TMEM columns: cross accumulators at 0 / 128, main accumulators at 256 / 384
+        const uint32_t d_cross = tmem_base + (uint32_t)(T2_BN * cx);
+        mbar_wait(cempty_bar(cx), ((itemc >> 1) & 1) ^ 1);
         tc_fence_after();
         bool cross_started = false;
         for (int kc0 = item.kb0; kc0 < item.kb1; kc0 += p.drain_kb, ++chain) {
           const int kc1 = min(item.kb1, kc0 + p.drain_kb);
-          const int j = chain % 3;
-          const uint32_t d_main = tmem_base + (uint32_t)(T2_BN * (1 + j));
-          mbar_wait(tempty_bar(j), ((chain / 3) & 1) ^ 1);
+          const int j = chain & 1;
+          const uint32_t d_main = tmem_base + (uint32_t)(T2_BN * (2 + j));
+          mbar_wait(tempty_bar(j), ((chain >> 1) & 1) ^ 1);
           tc_fence_after();
           for (int kb = kc0; kb < kc1; ++kb, ++it) {
             const int st = it % T2_STAGES;
@@ -262,7 +266,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           }
           umma_commit(tfull_bar(j));
         }
-        umma_commit(cfull_bar);
+        umma_commit(cfull_bar(cx));
       }
     }
   } else if (warp >= 8 && warp < 12) {
@@ -311,15 +315,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = 0.f;
       for (int kc0 = item.kb0; kc0 < item.kb1; kc0 += p.drain_kb, ++chain) {
-        const int j = chain % 3;
-        mbar_wait(tfull_bar(j), (chain / 3) & 1);
+        const int j = chain & 1;
+        mbar_wait(tfull_bar(j), (chain >> 1) & 1);
         tc_fence_after();
         uint32_t r[32];
-        T2_TMEM_LD32(r, lane_addr + (uint32_t)(T2_BN * (1 + j)));
+        T2_TMEM_LD32(r, lane_addr + (uint32_t)(T2_BN * (2 + j)));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(r[i]);
-        T2_TMEM_LD32(r, lane_addr + (uint32_t)(T2_BN * (1 + j)) + 32u);
+        T2_TMEM_LD32(r, lane_addr + (uint32_t)(T2_BN * (2 + j)) + 32u);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         tc_fence_before();
         mbar_arrive(tempty_bar(j));   // the accumulator is free again as soon as it sits in registers
@@ -327,17 +331,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         for (int i = 0; i < 32; ++i) acc[32 + i] += __uint_as_float(r[i]);
       }
       {
-        mbar_wait(cfull_bar, itemc & 1);
+        const int cx = itemc & 1;
+        mbar_wait(cfull_bar(cx), (itemc >> 1) & 1);
         tc_fence_after();
         uint32_t r[32];
-        T2_TMEM_LD32(r, lane_addr);
+        T2_TMEM_LD32(r, lane_addr + (uint32_t)(T2_BN * cx));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(r[i]);
-        T2_TMEM_LD32(r, lane_addr + 32u);
+        T2_TMEM_LD32(r, lane_addr + (uint32_t)(T2_BN * cx) + 32u);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         tc_fence_before();
-        mbar_arrive(cempty_bar);
+        mbar_arrive(cempty_bar(cx));
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[32 + i] += __uint_as_float(r[i]);
       }

@@ -48,6 +48,19 @@ def _structure(edge_index, n, mode, ptr=None):
     return ops.graph_csr(edge_index, n, mode, ptr)
 
 
+def _pad4(x, weights):
+    """Zero-pad the feature axis of ``x`` and the input axis of ``weights`` to a multiple of 4 floats (16-byte rows) so the
+    vector hop kernels and the tensor-core GEMM take layers whose input width is not one (21 / 25 in everyday.json).
+    The padding columns are exact zeros end to end; ``F.pad`` keeps autograd (the gradients are sliced back)."""
+    pad = (-x.shape[1]) % 4
+    if pad == 0 or not PAD_INPUT_WIDTH:
+        return x, weights
+    return nn.functional.pad(x, (0, pad)), [nn.functional.pad(w, (0, pad)) for w in weights]
+
+
+PAD_INPUT_WIDTH = True
+
+
 # ------------------------------------------------------------------------------- TAGConv
 class _TAGConvFn(torch.autograd.Function):
     """out = act( sum_k A_hat^k X W_k^T + b ).  Forward: K hops (dc_spmm) + one multi-segment GEMM
@@ -113,11 +126,11 @@ class TAGConv(nn.Module):
         self.precision = precision
 
     def forward(self, x, edge_index, relu=False, ptr=None):
+        x, ws = _pad4(x, [l.weight for l in self.lins])
         if USE_TORCH_OPS and isinstance(edge_index, torch.Tensor):
-            return torch.ops.dcb200.tag_conv(x, edge_index, [l.weight for l in self.lins], self.bias, relu, self.normalize,
-                                             self.precision, ptr)[0]
+            return torch.ops.dcb200.tag_conv(x, edge_index, ws, self.bias, relu, self.normalize, self.precision, ptr)[0]
         g = _structure(edge_index, x.shape[0], "tag" if self.normalize else "plain", ptr)
-        return _TAGConvFn.apply(x, g, self.bias, relu, self.precision, *[l.weight for l in self.lins])
+        return _TAGConvFn.apply(x, g, self.bias, relu, self.precision, *ws)
 
 
 # ------------------------------------------------------------------------------- GCNConv
