@@ -22,6 +22,11 @@ class GemmSeg(C.Structure):
     _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("B", C.c_void_p), ("ldb", C.c_int64), ("K", C.c_int64)]
 
 
+class GemmProblem(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("B", C.c_void_p), ("ldb", C.c_int64), ("C", C.c_void_p), ("ldc", C.c_int64),
+                ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64)]
+
+
 _p, _i64, _i32, _f32, _sz, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t, C.c_int
 
 # name -> (restype, argtypes); mirrors include/dcb200.h one to one
@@ -44,6 +49,8 @@ PROTOTYPES = {
     "dc_edge_relu": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _int, _p]),
     "dc_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _int, _int]),
     "dc_gemm": (_int, [C.POINTER(GemmSeg), _int, _int, _int, _i64, _i64, _p, _i64, _p, _int, _int, _int, _p, _sz, _p]),
+    "dc_gemm_batched_workspace_bytes": (_sz, [_i32]),
+    "dc_gemm_batched": (_int, [C.POINTER(GemmProblem), _i32, _int, _int, _int, _int, _p, _sz, _p]),
     "dc_colsum_workspace_bytes": (_sz, [_i64, _i64]),
     "dc_colsum": (_int, [_p, _i64, _i64, _i64, _p, _p, _sz, _p]),
     "dc_softmax_rows": (_int, [_p, _i64, _i64, _i64, _p]),

@@ -6,8 +6,8 @@ Per head (one shared ``nn.Linear`` L for queries and keys, no 1/sqrt(d) scale, v
 
 Everything runs in libdcb200 through the C ABI: the two projections are one GEMM each over all nodes of the
 batch; inside every attention group (``attn_group`` graphs, see model.py) the score matrix, its softmax and the
-two products with it are ``dc_gemm`` (N-chunked tcgen05 kind::tf32 with the 3-term split, fp32-class accuracy)
-and ``dc_softmax_rows`` / ``dc_softmax_bwd_rows``.  Backward is hand-derived (one ``autograd.Function`` per
+two products with it are ``dc_gemm_batched`` (one launch of the tcgen05 kind::tf32 kernel with the 3-term split per
+product type over ALL groups, fp32-class accuracy) and ``dc_softmax_rows`` / ``dc_softmax_bwd_rows``.  Backward is hand-derived (one ``autograd.Function`` per
 head): dP = dO Xr^T, dXr = P^T dO, dS = P o (dP - rowsum(dP o P)), dQ = dS K, dK = dS^T Q, then the projection
 gradients over all nodes at once.  The attention weights of a group are kept for backward ([ns, nr] fp32).
 """
@@ -47,23 +47,23 @@ class _AttnHeadFn(torch.autograd.Function):
         q = ops.gemm([(xs, W)], Ns, F, trans_b=True, bias=b)     # L(x_resting)  [Ns, F]
         k = ops.gemm([(xr, W)], Nr, F, trans_b=True, bias=b)     # L(x_rigid)    [Nr, F]
         out = torch.empty((Ns, F), dtype=_f32, device=xs.device)
-        probs = []
+        live, probs = [], []
         for s0, s1, r0, r1 in groups:
             ns, nr = s1 - s0, r1 - r0
             if ns == 0:
-                probs.append(None)
                 continue
-            if nr == 0:   # softmax over an empty set: the reference would produce NaN-free zeros from an empty mm
+            if nr == 0:   # softmax over an empty set: the reference's empty mm gives zeros
                 out[s0:s1].zero_()
-                probs.append(None)
                 continue
-            P = torch.empty((ns, (nr + 3) // 4 * 4), dtype=_f32, device=xs.device)[:, :nr]   # 16-byte aligned rows
-            ops.gemm([(q[s0:s1], k[r0:r1])], ns, nr, trans_b=True, out=P)        # scores
+            live.append((s0, s1, r0, r1))
+            probs.append(torch.empty((ns, (nr + 3) // 4 * 4), dtype=_f32, device=xs.device)[:, :nr])   # 16-byte aligned rows
+        # one batched tensor-core launch per product type over all groups
+        ops.gemm_batched([(q[s0:s1], k[r0:r1], P) for (s0, s1, r0, r1), P in zip(live, probs)], trans_b=True)       # scores
+        for P in probs:
             softmax_rows_(P)
-            ops.gemm([(P, xr[r0:r1])], ns, F, trans_b=False, out=out[s0:s1])     # attn @ x_rigid
-            probs.append(P)
+        ops.gemm_batched([(P, xr[r0:r1], out[s0:s1]) for (s0, s1, r0, r1), P in zip(live, probs)], trans_b=False)   # attn @ x_rigid
         ctx.save_for_backward(xs, xr, W, q, k)
-        ctx.probs, ctx.groups = probs, groups
+        ctx.probs, ctx.groups = probs, live
         return out
 
     @staticmethod
@@ -72,20 +72,18 @@ class _AttnHeadFn(torch.autograd.Function):
         dout = dout.contiguous()
         Ns, F = xs.shape
         Nr = xr.shape[0]
+        groups, probs = ctx.groups, ctx.probs
         dq = torch.zeros((Ns, F), dtype=_f32, device=xs.device)
         dk = torch.zeros((Nr, F), dtype=_f32, device=xs.device)
         dxr = torch.zeros((Nr, F), dtype=_f32, device=xs.device)
-        for (s0, s1, r0, r1), P in zip(ctx.groups, ctx.probs):
-            if P is None:
-                continue
-            ns, nr = s1 - s0, r1 - r0
-            dO = dout[s0:s1]
-            dP = torch.empty_like(P.as_strided((ns, P.stride(0)), (P.stride(0), 1)))[:, :nr]
-            ops.gemm([(dO, xr[r0:r1])], ns, nr, trans_b=True, out=dP)                                # dO Xr^T
-            ops.gemm([(P, dO)], nr, F, trans_a=True, trans_b=False, out=dxr[r0:r1], precision=ATTN_TN_PRECISION)   # P^T dO
-            softmax_bwd_rows_(P, dP)                                                                  # dS (in dP)
-            ops.gemm([(dP, k[r0:r1])], ns, F, trans_b=False, out=dq[s0:s1])                           # dS K
-            ops.gemm([(dP, q[s0:s1])], nr, F, trans_a=True, trans_b=False, out=dk[r0:r1], precision=ATTN_TN_PRECISION)   # dS^T Q
+        dPs = [torch.empty((P.shape[0], P.stride(0)), dtype=_f32, device=xs.device)[:, :P.shape[1]] for P in probs]
+        G = list(zip(groups, probs, dPs))
+        ops.gemm_batched([(dout[s0:s1], xr[r0:r1], dP) for (s0, s1, r0, r1), P, dP in G], trans_b=True)                       # dP = dO Xr^T
+        ops.gemm_batched([(P, dout[s0:s1], dxr[r0:r1]) for (s0, s1, r0, r1), P, dP in G], trans_a=True, trans_b=False)       # dXr = P^T dO
+        for _, P, dP in G:
+            softmax_bwd_rows_(P, dP)                                                                                           # dS (in dP)
+        ops.gemm_batched([(dP, k[r0:r1], dq[s0:s1]) for (s0, s1, r0, r1), P, dP in G], trans_b=False)                         # dQ = dS K
+        ops.gemm_batched([(dP, q[s0:s1], dk[r0:r1]) for (s0, s1, r0, r1), P, dP in G], trans_a=True, trans_b=False)           # dK = dS^T Q
         ctx.probs = None
         # projections: q = xs W^T + b, k = xr W^T + b
         dxs = ops.gemm([(dq, W)], Ns, F, trans_b=False)
@@ -94,11 +92,6 @@ class _AttnHeadFn(torch.autograd.Function):
         ops.gemm([(dk, xr)], F, F, trans_a=True, trans_b=False, out=dW, accumulate=True)
         db = ops.colsum(dq) + ops.colsum(dk)
         return dxs, dxr, dW, db, None
-
-
-# precision of the two transposed products (contraction over the soft nodes of a group): the tcgen05 MN-major
-# kernel (K3) by default; DC_GEMM_FP32 selects the exact FFMA kernel
-ATTN_TN_PRECISION = _abi.GEMM_PREFER_TC
 
 
 def cross_attention(x_resting, x_rigid, heads, ptr_s, ptr_r, group=None, concat=True):

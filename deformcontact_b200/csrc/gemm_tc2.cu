@@ -19,6 +19,9 @@
 //     is cut into parts whose partial tiles go to slabs that a second kernel sums in fixed order (deterministic).
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <vector>
 
 #include "common.cuh"
 
@@ -36,7 +39,19 @@ constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOAT
 constexpr int T2_DRAIN_KB = 8;                                // chain length in k-blocks (32 MMA steps)
 constexpr int T2_MAX_KPARTS = 16;
 
+// one problem of a batched launch (device table; the tensor maps are read by TMA straight from global memory)
+struct alignas(64) T2Problem {
+  CUtensorMap mapA, mapB;
+  float* C;
+  long long ldc;
+  int M, N, kb_total, n_chunks;
+  int pad[8];
+};
+
 struct T2Params {
+  const T2Problem* batch;   // != nullptr: batched launch (single segment, no k parts); item_off[i] = first item of problem i
+  const int* item_off;
+  int n_problems;
   int nseg;
   int kb_seg[4];          // k-blocks per segment
   int kb_total;
@@ -132,15 +147,36 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
 
 struct T2Item {
   int m0, n0, part, kb0, kb1;
+  int M, N;
+  float* C;
+  long long ldc;
+  const CUtensorMap *mapA, *mapB;   // batched launches only
 };
-__device__ __forceinline__ T2Item t2_item(const T2Params& p, int w) {
+// work item w of this CTA's sequence (w increases monotonically, so the problem index only moves forward)
+__device__ __forceinline__ T2Item t2_item(const T2Params& p, int w, int& pidx) {
   T2Item it;
+  if (p.batch) {
+    while (w >= p.item_off[pidx + 1]) ++pidx;
+    const T2Problem* q = p.batch + pidx;
+    const int local = w - p.item_off[pidx];
+    const int nch = q->n_chunks;
+    it.part = 0;
+    it.n0 = (local % nch) * T2_BN;
+    it.m0 = (local / nch) * T2_BM;
+    it.kb0 = 0;
+    it.kb1 = q->kb_total;
+    it.M = q->M; it.N = q->N; it.C = q->C; it.ldc = q->ldc;
+    it.mapA = &q->mapA; it.mapB = &q->mapB;
+    return it;
+  }
   it.part = w % p.k_parts;
   const int mn = w / p.k_parts;
   it.n0 = (mn % p.n_chunks) * T2_BN;
   it.m0 = (mn / p.n_chunks) * T2_BM;
   it.kb0 = it.part * p.kb_per_part;
   it.kb1 = min(p.kb_total, it.kb0 + p.kb_per_part);
+  it.M = p.M; it.N = p.N; it.C = p.C; it.ldc = p.ldc;
+  it.mapA = nullptr; it.mapB = nullptr;
   return it;
 }
 
@@ -196,12 +232,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     if (lane == 0) {
       const CUtensorMap* mA[4] = {&mapA0, &mapA1, &mapA2, &mapA3};
       const CUtensorMap* mB[4] = {&mapB0, &mapB1, &mapB2, &mapB3};
-      int it = 0;
+      int it = 0, pidx = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
-        const T2Item item = t2_item(p, w);
+        const T2Item item = t2_item(p, w, pidx);
+        if (p.batch) { mA[0] = item.mapA; mB[0] = item.mapB; }
         int seg = 0, seg_kb0 = 0;   // segment containing k-block kb, and its first k-block
         for (int kb = item.kb0; kb < item.kb1; ++kb, ++it) {
-          while (kb >= seg_kb0 + p.kb_seg[seg]) { seg_kb0 += p.kb_seg[seg]; ++seg; }
+          if (!p.batch)
+            while (kb >= seg_kb0 + p.kb_seg[seg]) { seg_kb0 += p.kb_seg[seg]; ++seg; }
           const int k0 = (kb - seg_kb0) * T2_BK;
           const int st = it % T2_STAGES;
           const uint32_t ph = (it / T2_STAGES) & 1;
@@ -229,9 +267,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                              ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
       const uint32_t a_adv = p.a_mn ? (1024u >> 4) : (32u >> 4), b_adv = p.b_mn ? (1024u >> 4) : (32u >> 4);
-      int it = 0, chain = 0, itemc = 0;
+      int it = 0, chain = 0, itemc = 0, pidx = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++itemc) {
-        const T2Item item = t2_item(p, w);
+        const T2Item item = t2_item(p, w, pidx);
         const int cx = itemc & 1;   // TMEM columns: cross accumulators at 0 / 128, main accumulators at 256 / 384
         const uint32_t d_cross = tmem_base + (uint32_t)(T2_BN * cx);
         mbar_wait(cempty_bar(cx), ((itemc >> 1) & 1) ^ 1);
@@ -272,9 +310,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   } else if (warp >= 8 && warp < 12) {
     // ------------------------------------------------------------------ split warps: X -> X_hi (in place), X_lo
     const int t = threadIdx.x - 256;
-    int it = 0;
+    int it = 0, pidx = 0;
     for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
-      const T2Item item = t2_item(p, w);
+      const T2Item item = t2_item(p, w, pidx);
       for (int kb = item.kb0; kb < item.kb1; ++kb, ++it) {
         const int st = it % T2_STAGES;
         const uint32_t ph = (it / T2_STAGES) & 1;
@@ -305,12 +343,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const int q = warp & 3;               // TMEM lane quarter == warp % 4
     const int half = warp >= 12 ? 1 : 0;
     float* stg = epi_stage + ((half * 4) + q) * T2_EPI_WARP_FLOATS;
-    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-                        (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) && ((p.N & 3) == 0 || p.k_parts == 1);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
-    int chain = 0, itemc = 0;
+    int chain = 0, itemc = 0, pidx = 0;
     for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++itemc) {
-      const T2Item item = t2_item(p, w);
+      const T2Item item = t2_item(p, w, pidx);
+      const bool vec_ok = ((item.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(item.C) & 15) == 0) &&
+                          (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) && ((item.N & 3) == 0 || p.k_parts == 1);
       float acc[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = 0.f;
@@ -348,8 +386,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       }
       // ---- write the 32 x 64 block of this warp, 16 columns at a time through a padded staging tile
       const bool to_slab = p.k_parts > 1;
-      float* outp = to_slab ? p.partial + (size_t)item.part * (size_t)p.M * p.N : p.C;
-      const long long ldo = to_slab ? (long long)p.N : p.ldc;
+      float* outp = to_slab ? p.partial + (size_t)item.part * (size_t)item.M * item.N : item.C;
+      const long long ldo = to_slab ? (long long)item.N : item.ldc;
       const bool add_c = !to_slab && p.accumulate;
       const bool do_relu = !to_slab && p.relu;
       const float* bias = to_slab ? nullptr : p.bias;
@@ -362,13 +400,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         __syncwarp();
         const int c4 = (lane & 3) * 4;
         const int col = item.n0 + half * 64 + g * 16 + c4;
-        if (vec_ok && col + 3 < p.N) {
+        if (vec_ok && col + 3 < item.N) {
           const float4 bv = bias ? *reinterpret_cast<const float4*>(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int it4 = 0; it4 < 4; ++it4) {
             const int rr = it4 * 8 + (lane >> 2);
             const int row = row0 + rr;
-            if (row < p.M) {
+            if (row < item.M) {
               float4 v = *reinterpret_cast<const float4*>(stg + rr * T2_EPI_ROW + c4);
               v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
               float4* dst = reinterpret_cast<float4*>(outp + (long long)row * ldo + col);
@@ -382,7 +420,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             const int rr = it4 * 8 + (lane >> 2);
             const int row = row0 + rr;
             for (int e = 0; e < 4; ++e) {
-              if (row < p.M && col + e < p.N) {
+              if (row < item.M && col + e < item.N) {
                 float v = stg[rr * T2_EPI_ROW + c4 + e] + (bias ? bias[col + e] : 0.f);
                 float* dst = outp + (long long)row * ldo + col + e;
                 if (add_c) v += *dst;
@@ -536,6 +574,84 @@ int gemm_tc2(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t 
     t2_reduce_kernel<<<(unsigned)cdiv(MN, 256), 256, 0, st>>>(p.partial, p.k_parts, MN, (int)N, C, ldc, bias, relu, accumulate);
     DC_LAUNCH_CHECK();
   }
+  return DC_OK;
+}
+
+size_t gemm_tc2_batched_workspace_bytes(int count) {
+  if (count < 0) count = 0;
+  return align_up((size_t)count * sizeof(T2Problem), 256) + align_up((size_t)(count + 1) * sizeof(int), 256) + 512;
+}
+
+// `count` independent single-segment problems with common transposes in ONE persistent launch: work items of all
+// problems are dealt to the CTAs round-robin, so problems that are too small to fill the machine alone (the
+// per-group attention products) run at the rate of a large one.  The problem table (tensor maps + sizes) is built
+// on the host and copied into `workspace` on the stream.
+int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int transB, int relu, int accumulate, void* workspace,
+                     size_t workspace_bytes, cudaStream_t st) {
+  DC_REQUIRE(probs && count > 0, DC_EINVAL, "gemm_batched: no problems");
+  const size_t need = gemm_tc2_batched_workspace_bytes(count);
+  DC_REQUIRE(workspace && workspace_bytes >= need, DC_EWORKSPACE, "gemm_batched: workspace %zu < %zu", workspace_bytes, need);
+  const size_t tab_bytes = align_up((size_t)count * sizeof(T2Problem), 256);
+  const size_t off_bytes = (size_t)(count + 1) * sizeof(int);
+  // host image of the table (tensor maps must be 64-byte aligned in device memory: the workspace is aligned to 256)
+  std::vector<unsigned char> host(tab_bytes + off_bytes + 64);
+  unsigned char* hbase = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(host.data()) + 63) & ~(uintptr_t)63);
+  T2Problem* tab = reinterpret_cast<T2Problem*>(hbase);
+  int* item_off = reinterpret_cast<int*>(hbase + tab_bytes);
+  int64_t items = 0;
+  for (int i = 0; i < count; ++i) {
+    const dc_gemm_problem& q = probs[i];
+    DC_REQUIRE(q.M >= 0 && q.N >= 0 && q.K >= 0, DC_EINVAL, "gemm_batched: negative size in problem %d", i);
+    item_off[i] = (int)items;
+    T2Problem& t = tab[i];
+    memset(&t, 0, sizeof(t));
+    if (q.M == 0 || q.N == 0) continue;   // empty problem: no items
+    DC_REQUIRE(q.K > 0, DC_ENOSUP, "gemm_batched: K = 0 in problem %d (zero the output instead)", i);
+    dc_gemm_seg seg{q.A, q.lda, q.B, q.ldb, q.K};
+    DC_REQUIRE(gemm_tc2_supported(&seg, 1, transA, transB, q.M, q.N) && q.C && q.ldc >= q.N, DC_ENOSUP,
+               "gemm_batched: problem %d is not supported by the tcgen05 path (needs lda/ldb %% 4 == 0, 16-byte aligned operands)", i);
+    if (transA) {
+      if (int rc = make_map2(&t.mapA, q.A, (uint64_t)q.M, (uint64_t)q.K, (uint64_t)q.lda, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+    } else {
+      if (int rc = make_map2(&t.mapA, q.A, (uint64_t)q.K, (uint64_t)q.M, (uint64_t)q.lda, T2_BM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    }
+    if (transB) {
+      if (int rc = make_map2(&t.mapB, q.B, (uint64_t)q.K, (uint64_t)q.N, (uint64_t)q.ldb, T2_BN, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    } else {
+      if (int rc = make_map2(&t.mapB, q.B, (uint64_t)q.N, (uint64_t)q.K, (uint64_t)q.ldb, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+    }
+    t.C = q.C; t.ldc = q.ldc; t.M = (int)q.M; t.N = (int)q.N;
+    t.kb_total = (int)cdiv(q.K, T2_BK);
+    t.n_chunks = (int)cdiv(q.N, T2_BN);
+    items += cdiv(q.M, T2_BM) * t.n_chunks;
+    DC_REQUIRE(items < (1ll << 30), DC_ENOSUP, "gemm_batched: too many work items");
+  }
+  item_off[count] = (int)items;
+  if (items == 0) return DC_OK;
+  unsigned char* dbase = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  DC_CUDA(cudaMemcpyAsync(dbase, hbase, tab_bytes + off_bytes, cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+  T2Params p{};
+  p.batch = reinterpret_cast<const T2Problem*>(dbase);
+  p.item_off = reinterpret_cast<const int*>(dbase + tab_bytes);
+  p.n_problems = count;
+  p.nseg = 1;
+  p.kb_seg[0] = 1 << 30;
+  p.a_mn = transA ? 1 : 0;
+  p.b_mn = transB ? 0 : 1;
+  p.k_parts = 1;
+  p.items = (int)items;
+  p.drain_kb = T2_DRAIN_KB;
+  p.relu = relu; p.accumulate = accumulate;
+  p.raw_hi = 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = p.items < kSMs ? p.items : kSMs;
+  CUtensorMap dummy{};
+  gemm_tc2_kernel<<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(dummy, dummy, dummy, dummy, dummy, dummy, dummy, dummy, p);
+  DC_LAUNCH_CHECK();
   return DC_OK;
 }
 

@@ -413,6 +413,39 @@ def gemm(segs, M, N, trans_a=False, trans_b=True, bias=None, relu=False, out=Non
     return out
 
 
+def gemm_batched(problems, trans_a=False, trans_b=True, relu=False, accumulate=False):
+    """problems = [(A, B, C), ...]: C_i = act(opA(A_i) opB(B_i)) (+C_i) for all i in one tensor-core launch; see
+    dc_gemm_batched.  Falls back to one dc_gemm per problem when a problem does not fit the tensor path."""
+    problems = [q for q in problems if q[2].numel() > 0]
+    if not problems:
+        return
+    arr = (_abi.GemmProblem * len(problems))()
+    flops = 0.0
+    ok = True
+    for i, (A, B, Cm) in enumerate(problems):
+        _need(A, _f32, "A"), _need(B, _f32, "B"), _need(Cm, _f32, "C")
+        lda, ldb, ldc = _rows(A, "A"), _rows(B, "B"), _rows(Cm, "C")
+        K = A.shape[0] if trans_a else A.shape[1]
+        Kb = B.shape[1] if trans_b else B.shape[0]
+        M = A.shape[1] if trans_a else A.shape[0]
+        N = B.shape[0] if trans_b else B.shape[1]
+        if K != Kb or tuple(Cm.shape) != (M, N):
+            raise _abi.DcError(f"gemm_batched: problem {i}: {tuple(A.shape)} x {tuple(B.shape)} -> {tuple(Cm.shape)}")
+        ok = ok and K > 0 and lda % 4 == 0 and ldb % 4 == 0 and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0
+        arr[i] = _abi.GemmProblem(A.data_ptr(), lda, B.data_ptr(), ldb, Cm.data_ptr(), ldc, M, N, K)
+        flops += 2.0 * M * N * K
+    if not ok:
+        for A, B, Cm in problems:
+            gemm([(A, B)], Cm.shape[0], Cm.shape[1], trans_a=trans_a, trans_b=trans_b, relu=relu, out=Cm, accumulate=accumulate)
+        return
+    nb = _abi.lib().dc_gemm_batched_workspace_bytes(len(problems))
+    ws = _workspace(nb, problems[0][0].device)
+    e0 = _prof_begin()
+    _abi.call("dc_gemm_batched", arr, len(problems), int(trans_a), int(trans_b), int(bool(relu)), int(bool(accumulate)), _ptr(ws), nb,
+              _stream())
+    _prof_end(e0, op="gemm", M=0, N=0, K=0, flops=flops)
+
+
 def colsum(X):
     _need(X, _f32, "X")
     ldx = _rows(X, "X")

@@ -180,6 +180,25 @@ DC_API int dc_gemm(const dc_gemm_seg* segs /*host array*/, int nseg, int transA,
             float* C, int64_t ldc, const float* bias, int relu, int accumulate, int precision, void* workspace,
             size_t workspace_bytes, dc_stream_t stream);
 
+/* `count` independent products C_i[M_i,N_i] = act(opA(A_i) opB(B_i)) (+C_i) with common transposes in ONE launch of the
+ * tcgen05 3xTF32 kernel: the 128 x 128 work items of all problems are dealt to the persistent CTAs together, so
+ * problems too small to fill 148 SMs alone (the per-group products of the cross attention, models/model.py:16-18) run
+ * at the rate of a large one.  Every problem must satisfy the tensor-path requirements of dc_gemm (DC_ENOSUP
+ * otherwise; the caller then falls back to per-problem dc_gemm).  `problems` is a host array; the problem table
+ * (tensor maps) is staged through `workspace`. */
+typedef struct {
+  const float* A;
+  int64_t lda;
+  const float* B;
+  int64_t ldb;
+  float* C;
+  int64_t ldc;
+  int64_t M, N, K;
+} dc_gemm_problem;
+DC_API size_t dc_gemm_batched_workspace_bytes(int32_t count);
+DC_API int dc_gemm_batched(const dc_gemm_problem* problems /*host array*/, int32_t count, int transA, int transB, int relu,
+                           int accumulate, void* workspace, size_t workspace_bytes, dc_stream_t stream);
+
 /* colsum[n] = sum_m X[m, n] (bias gradient), deterministic two-stage tree. */
 DC_API size_t dc_colsum_workspace_bytes(int64_t M, int64_t N);
 DC_API int dc_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* workspace,

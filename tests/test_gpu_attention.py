@@ -110,3 +110,36 @@ def test_mlp_linear_segments(dc, widths, N, relu):
     ours, r32, r64 = run(torch.float32, "cuda"), run(torch.float32, "cpu"), run(torch.float64, "cpu")
     for i, (a, b32, b64) in enumerate(zip(ours, r32, r64)):
         assert_close_arbiter(a, b32, b64, what=f"linear tensor {i}")
+
+
+def test_gemm_batched(dc):
+    """dc_gemm_batched == per-problem dc_gemm (same kernel, same chain structure => bit-identical), every layout,
+    ragged sizes, empty problems, and the fallback when a problem does not fit the tensor path."""
+    from deformcontact_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    shapes = [(300, 520, 256), (1, 17, 40), (129, 128, 3048), (1000, 256, 36), (0, 64, 64), (257, 64, 8)]
+    for ta in (False, True):
+        for tb in (False, True):
+            probs, refs = [], []
+            for M, N, K in shapes:
+                A = torch.randn((K, (M + 3) // 4 * 4) if ta else (M, K), generator=g).cuda()
+                if ta:
+                    A = A[:, :M]
+                B = (torch.randn(N, K, generator=g) if tb else torch.randn(K, (N + 3) // 4 * 4, generator=g)).cuda()
+                if not tb:
+                    B = B[:, :N]
+                Cm = torch.zeros(M, N).cuda()
+                probs.append((A, B, Cm))
+                refs.append(ops.gemm([(A, B)], M, N, trans_a=ta, trans_b=tb, precision=dc._abi.GEMM_TF32X3) if M else Cm.clone())
+            ops.gemm_batched(probs, trans_a=ta, trans_b=tb)
+            for (A, B, Cm), ref, (M, N, K) in zip(probs, refs, shapes):
+                if M == 129 and K == 3048:
+                    # the single-problem launch splits K into parts (different summation tree): compare against fp64
+                    r64 = (A.double().T if ta else A.double()) @ (B.double().T if tb else B.double())
+                    assert_close(Cm, r64.float(), what="batched vs fp64")
+                else:
+                    assert torch.equal(Cm, ref), (ta, tb, M, N, K)
+    # a problem with an unaligned leading dimension sends the whole batch down the per-problem path
+    A = torch.randn(64, 21, generator=g).cuda(); B = torch.randn(32, 21, generator=g).cuda(); Cm = torch.empty(64, 32).cuda()
+    ops.gemm_batched([(A, B, Cm)], trans_b=True)
+    assert_close(Cm, (A.double() @ B.double().T).float(), what="fallback")
