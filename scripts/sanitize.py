@@ -12,12 +12,20 @@ for backbone in ("TAGConv", "GCNConv", "GATConv", "MPNN"):
 pos = torch.rand(700, 3, device="cuda")
 dc.knn_graph(pos, 40); dc.radius_graph(pos, 0.2)
 x = torch.randn(rest.x.shape[0], 256, device="cuda", requires_grad=True)
-for variant in ("generic", "tiled", "tiled8", "tiled_prefetch", "smem"):
+for variant in ("generic", "tiled", "tiled8", "tiled_prefetch", "smem", "lean", "blocks", "auto"):
     ops.K1_VARIANT = variant
     ops.clear_csr_cache()
     layer = dc.TAGConv(256, 256, precision=ops.GEMM_PREFER_TC).cuda()
     layer(x, rest.edge_index, relu=True, ptr=rest._ptr_host).sum().backward()
 A = torch.randn(3000, 256, device="cuda"); B = torch.randn(3000, 64, device="cuda")
 ops.gemm([(A, B)], 256, 64, True, False, precision=ops.GEMM_TF32X3)
+# K2 v2: every layout, column chunks, ragged K, split-K slabs, batched launch
+for ta in (False, True):
+    for tb in (False, True):
+        M, N, K = 300, 520, 200
+        A = torch.randn((K, M) if ta else (M, K), device="cuda"); B = torch.randn((N, K) if tb else (K, N), device="cuda")
+        ops.gemm([(A, B)], M, N, ta, tb, precision=ops.GEMM_TF32X3)
+        ops.gemm_batched([(A, B, torch.empty(M, N, device="cuda")), (A, B, torch.empty(M, N, device="cuda"))], ta, tb)
+ops.gemm([(torch.randn(130, 3048, device="cuda"), torch.randn(64, 3048, device="cuda"))], 130, 64, False, True, precision=ops.GEMM_TF32X3)
 torch.cuda.synchronize()
 print("sanitize run ok")
