@@ -7,9 +7,12 @@
 //   * The tensor core truncates its fp32 TMEM accumulator on every MMA, so an accumulation chain is cut every
 //     `drain_kb` k-blocks.  v1 drained a chain by read-modify-writing the C tile in global memory while the MMA
 //     pipe waited (45 % of the kernel at K = 1024, 60 % at K = 3048).  Here a tile is 128 x 128, TMEM holds two
-//     main accumulators (alternating per chain) and two cross-term accumulators (alternating per work item), and
-//     the eight epilogue warps add finished chains into REGISTERS (64 fp32 per thread, round-to-nearest) while the
-//     next chain / the next item runs: no global traffic, no MMA stall; C is written once.
+//     accumulator pairs [main | cross terms] (256 columns each, alternating per chain), and the eight epilogue
+//     warps add finished chains into REGISTERS (64 fp32 per thread, round-to-nearest) while the next chain runs:
+//     no global traffic, no MMA stall; C is written once.
+//   * The B_lo tile sits right behind the B_hi tile in shared memory, so A_hi [B_hi ; B_lo]^T is ONE N = 256 MMA that
+//     fills main and cross halves at once; a second N = 128 MMA adds A_lo B_hi^T to the cross half: two MMAs and 20 KB
+//     of operand reads per K = 8 step instead of three and 24 KB.
 //   * Both operands arrive as raw fp32 tiles by TMA and are split into hi / lo in shared memory (v1 loaded
 //     pre-split B_hi and B_lo: 80 KB per k-block, L2-bound at ~207 TFLOP/s; now 32 KB per k-block), so there is
 //     no packing pre-kernel and no workspace for it.
@@ -190,14 +193,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   float* epi_stage = reinterpret_cast<float*>(base_ptr + T2_STAGES * T2_STAGE_BYTES);
   const uint32_t bar_base = base + T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOATS * 4;
-  // barriers (8 B each): full[3], xform[3], empty[3], tfull[2], tempty[2], cfull[2], cempty[2]; then the TMEM pointer
+  // barriers (8 B each): full[3], xform[3], empty[3], tfull[2], tempty[2]; then the TMEM pointer
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto xform_bar = [&](int s) { return bar_base + 24u + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 48u + 8u * s; };
   auto tfull_bar = [&](int j) { return bar_base + 72u + 8u * j; };
   auto tempty_bar = [&](int j) { return bar_base + 88u + 8u * j; };
-  auto cfull_bar = [&](int c) { return bar_base + 104u + 8u * c; };
-  auto cempty_bar = [&](int c) { return bar_base + 120u + 8u * c; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOATS * 4 + 144);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -211,8 +212,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     for (int j = 0; j < 2; ++j) {
       mbar_init(tfull_bar(j), 1);
       mbar_init(tempty_bar(j), 256);
-      mbar_init(cfull_bar(j), 1);
-      mbar_init(cempty_bar(j), 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -267,18 +266,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                              ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
       const uint32_t a_adv = p.a_mn ? (1024u >> 4) : (32u >> 4), b_adv = p.b_mn ? (1024u >> 4) : (32u >> 4);
-      int it = 0, chain = 0, itemc = 0, pidx = 0;
-      for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++itemc) {
+      // N = 256 form of the same descriptor: the B_lo tile follows the B_hi tile in shared memory (same canonical layout), so
+      // ONE MMA gives [ A_hi B_hi | A_hi B_lo ] in 256 adjacent TMEM columns; a second N = 128 MMA adds A_lo B_hi onto the
+      // cross half.  2 MMAs and 20 KB of operand reads per K = 8 step instead of 3 and 24 KB.
+      const uint32_t idesc256 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(2 * T2_BN >> 3) << 17);
+      int it = 0, chain = 0, pidx = 0;
+      for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
         const T2Item item = t2_item(p, w, pidx);
-        const int cx = itemc & 1;   // TMEM columns: cross accumulators at 0 / 128, main accumulators at 256 / 384
-        const uint32_t d_cross = tmem_base + (uint32_t)(T2_BN * cx);
-        mbar_wait(cempty_bar(cx), ((itemc >> 1) & 1) ^ 1);
-        tc_fence_after();
-        bool cross_started = false;
         for (int kc0 = item.kb0; kc0 < item.kb1; kc0 += p.drain_kb, ++chain) {
           const int kc1 = min(item.kb1, kc0 + p.drain_kb);
-          const int j = chain & 1;
-          const uint32_t d_main = tmem_base + (uint32_t)(T2_BN * (2 + j));
+          const int j = chain & 1;   // TMEM columns [256 j, 256 j + 128) main, [256 j + 128, 256 j + 256) cross terms
+          const uint32_t d_main = tmem_base + (uint32_t)(2 * T2_BN * j), d_cross = d_main + (uint32_t)T2_BN;
           mbar_wait(tempty_bar(j), ((chain >> 1) & 1) ^ 1);
           tc_fence_after();
           for (int kb = kc0; kb < kc1; ++kb, ++it) {
@@ -291,20 +289,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             const uint64_t a_hi = p.a_mn ? desc_mnmajor(sbase) : desc_kmajor(sbase);
             const uint64_t a_lo = p.a_mn ? desc_mnmajor(sbase + T2_TILE_BYTES) : desc_kmajor(sbase + T2_TILE_BYTES);
             const uint64_t b_hi = p.b_mn ? desc_mnmajor(sbase + 2 * T2_TILE_BYTES) : desc_kmajor(sbase + 2 * T2_TILE_BYTES);
-            const uint64_t b_lo = p.b_mn ? desc_mnmajor(sbase + 3 * T2_TILE_BYTES) : desc_kmajor(sbase + 3 * T2_TILE_BYTES);
 #pragma unroll
             for (int kk = 0; kk < T2_BK / 8; ++kk) {
               const uint64_t aa = (uint64_t)(kk * a_adv), bb = (uint64_t)(kk * b_adv);
-              umma_tf32(d_cross, a_lo + aa, b_hi + bb, idesc, cross_started ? 1u : 0u);   // whole-item chain (tiny values)
-              cross_started = true;
-              umma_tf32(d_cross, a_hi + aa, b_lo + bb, idesc, 1u);
-              umma_tf32(d_main, a_hi + aa, b_hi + bb, idesc, (kb > kc0 || kk > 0) ? 1u : 0u);   // restarted every chain
+              const uint32_t acc = (kb > kc0 || kk > 0) ? 1u : 0u;   // both halves restart with every chain
+              umma_tf32(d_main, a_hi + aa, b_hi + bb, idesc256, acc);   // [main | A_hi B_lo]
+              umma_tf32(d_cross, a_lo + aa, b_hi + bb, idesc, 1u);      // cross += A_lo B_hi
             }
             umma_commit(empty_bar(st));
           }
           umma_commit(tfull_bar(j));
         }
-        umma_commit(cfull_bar(cx));
       }
     }
   } else if (warp >= 8 && warp < 12) {
@@ -344,8 +339,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const int half = warp >= 12 ? 1 : 0;
     float* stg = epi_stage + ((half * 4) + q) * T2_EPI_WARP_FLOATS;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
-    int chain = 0, itemc = 0, pidx = 0;
-    for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++itemc) {
+    int chain = 0, pidx = 0;
+    for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
       const T2Item item = t2_item(p, w, pidx);
       const bool vec_ok = ((item.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(item.C) & 15) == 0) &&
                           (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) && ((item.N & 3) == 0 || p.k_parts == 1);
@@ -356,33 +351,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         const int j = chain & 1;
         mbar_wait(tfull_bar(j), (chain >> 1) & 1);
         tc_fence_after();
+        const uint32_t cbase = lane_addr + (uint32_t)(2 * T2_BN * j);
         uint32_t r[32];
-        T2_TMEM_LD32(r, lane_addr + (uint32_t)(T2_BN * (2 + j)));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(r[i]);
-        T2_TMEM_LD32(r, lane_addr + (uint32_t)(T2_BN * (2 + j)) + 32u);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        mbar_arrive(tempty_bar(j));   // the accumulator is free again as soon as it sits in registers
+        for (int part = 0; part < 4; ++part) {   // main columns 0-31, 32-63 of this warp's half, then the cross-term columns
+          T2_TMEM_LD32(r, cbase + (uint32_t)((part >> 1) * T2_BN + (part & 1) * 32));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (part == 3) {
+            tc_fence_before();
+            mbar_arrive(tempty_bar(j));   // the accumulator pair is free again as soon as it sits in registers
+          }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[32 + i] += __uint_as_float(r[i]);
-      }
-      {
-        const int cx = itemc & 1;
-        mbar_wait(cfull_bar(cx), (itemc >> 1) & 1);
-        tc_fence_after();
-        uint32_t r[32];
-        T2_TMEM_LD32(r, lane_addr + (uint32_t)(T2_BN * cx));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(r[i]);
-        T2_TMEM_LD32(r, lane_addr + (uint32_t)(T2_BN * cx) + 32u);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        mbar_arrive(cempty_bar(cx));
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[32 + i] += __uint_as_float(r[i]);
+          for (int i = 0; i < 32; ++i) acc[(part & 1) * 32 + i] += __uint_as_float(r[i]);
+        }
       }
       // ---- write the 32 x 64 block of this warp, 16 columns at a time through a padded staging tile
       const bool to_slab = p.k_parts > 1;
