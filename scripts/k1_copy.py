@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from deformcontact_b200 import ops
 dev = torch.device("cuda", 0)
-B, n, F = 256, 2000, 256
+B, n, F = (int(sys.argv[1]), 2000, int(sys.argv[2])) if len(sys.argv) > 2 else (256, 2000, 256)
 N = B * n
 ei = torch.zeros(2, 0, dtype=torch.long, device=dev)
 G = ops.GraphCSR(ei, N, "tag", [i * n for i in range(B + 1)])
@@ -20,7 +20,7 @@ def t(fn, reps=20):
     return e0.elapsed_time(e1) / reps
 byt = 2 * N * F * 4
 print("torch copy_", round(byt / t(lambda: out.copy_(a)) / 1e6, 1), "GB/s")
-for v in ["generic", "lean", "blocks:0", "blocks:1", "blocks:4", "blocks:5"]:
+for v in ["generic", "lean", "blocks:4"]:
     name, _, fl = v.partition(":")
     ops.K1_VARIANT = name
     if fl: ops.K1_FLAGS = int(fl)
