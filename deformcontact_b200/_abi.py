@@ -24,7 +24,7 @@ class GemmSeg(C.Structure):
 
 class GemmProblem(C.Structure):
     _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("B", C.c_void_p), ("ldb", C.c_int64), ("C", C.c_void_p), ("ldc", C.c_int64),
-                ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64)]
+                ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("E", C.c_void_p), ("lde", C.c_int64), ("rowv", C.c_void_p)]
 
 
 _p, _i64, _i32, _f32, _sz, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t, C.c_int
@@ -53,6 +53,7 @@ PROTOTYPES = {
     "dc_gemm_batched": (_int, [C.POINTER(GemmProblem), _i32, _int, _int, _int, _int, _p, _sz, _p]),
     "dc_colsum_workspace_bytes": (_sz, [_i64, _i64]),
     "dc_colsum": (_int, [_p, _i64, _i64, _i64, _p, _p, _sz, _p]),
+    "dc_rowdot": (_int, [_p, _i64, _p, _i64, _i64, _i64, _p, _p]),
     "dc_softmax_rows": (_int, [_p, _i64, _i64, _i64, _p]),
     "dc_softmax_bwd_rows": (_int, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "dc_relu_bwd": (_int, [_p, _p, _p, _i64, _p]),

@@ -9,7 +9,8 @@ batch; inside every attention group (``attn_group`` graphs, see model.py) the sc
 two products with it are ``dc_gemm_batched`` (one launch of the tcgen05 kind::tf32 kernel with the 3-term split per
 product type over ALL groups, fp32-class accuracy) and ``dc_softmax_rows`` / ``dc_softmax_bwd_rows``.  Backward is hand-derived (one ``autograd.Function`` per
 head): dP = dO Xr^T, dXr = P^T dO, dS = P o (dP - rowsum(dP o P)), dQ = dS K, dK = dS^T Q, then the projection
-gradients over all nodes at once.  The attention weights of a group are kept for backward ([ns, nr] fp32).
+gradients over all nodes at once.  The softmax backward is fused into the epilogue of the dP product
+(``rowsum(dP o P) = rowdot(dO, O)``).  The attention weights of a group are kept for backward ([ns, nr] fp32).
 """
 import torch
 
@@ -62,13 +63,13 @@ class _AttnHeadFn(torch.autograd.Function):
         for P in probs:
             softmax_rows_(P)
         ops.gemm_batched([(P, xr[r0:r1], out[s0:s1]) for (s0, s1, r0, r1), P in zip(live, probs)], trans_b=False)   # attn @ x_rigid
-        ctx.save_for_backward(xs, xr, W, q, k)
+        ctx.save_for_backward(xs, xr, W, q, k, out)
         ctx.probs, ctx.groups = probs, live
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        xs, xr, W, q, k = ctx.saved_tensors
+        xs, xr, W, q, k, out = ctx.saved_tensors
         dout = dout.contiguous()
         Ns, F = xs.shape
         Nr = xr.shape[0]
@@ -78,10 +79,11 @@ class _AttnHeadFn(torch.autograd.Function):
         dxr = torch.zeros((Nr, F), dtype=_f32, device=xs.device)
         dPs = [torch.empty((P.shape[0], P.stride(0)), dtype=_f32, device=xs.device)[:, :P.shape[1]] for P in probs]
         G = list(zip(groups, probs, dPs))
-        ops.gemm_batched([(dout[s0:s1], xr[r0:r1], dP) for (s0, s1, r0, r1), P, dP in G], trans_b=True)                       # dP = dO Xr^T
+        # softmax backward dS = P o (dP - rowsum(dP o P)) fused into the epilogue of dP = dO Xr^T: the row sums equal
+        # rowdot(dO, O) because O = P Xr, so they are known before the product starts
+        D = ops.rowdot(dout, out)
+        ops.gemm_batched([(dout[s0:s1], xr[r0:r1], dP, P, D[s0:s1]) for (s0, s1, r0, r1), P, dP in G], trans_b=True)          # dS
         ops.gemm_batched([(P, dout[s0:s1], dxr[r0:r1]) for (s0, s1, r0, r1), P, dP in G], trans_a=True, trans_b=False)       # dXr = P^T dO
-        for _, P, dP in G:
-            softmax_bwd_rows_(P, dP)                                                                                           # dS (in dP)
         ops.gemm_batched([(dP, k[r0:r1], dq[s0:s1]) for (s0, s1, r0, r1), P, dP in G], trans_b=False)                         # dQ = dS K
         ops.gemm_batched([(dP, q[s0:s1], dk[r0:r1]) for (s0, s1, r0, r1), P, dP in G], trans_a=True, trans_b=False)           # dK = dS^T Q
         ctx.probs = None

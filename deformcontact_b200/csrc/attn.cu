@@ -104,7 +104,32 @@ softmax_bwd_rows_kernel(const float* __restrict__ P, long long ldp, float* __res
     for (int c = threadIdx.x; c < N; c += SM_THREADS) drow[c] = prow[c] * (drow[c] - dot);
   }
 }
+// out[m] = sum_n A[m, n] * B[m, n]; one warp per row, lane-strided partial sums + shuffle tree (fixed order)
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, long long M, int N,
+              float* __restrict__ out) {
+  const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float* a = A + row * lda;
+  const float* b = B + row * ldb;
+  float s = 0.f;
+  for (int c = lane; c < N; c += 32) s += a[c] * b[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[row] = s;
+}
 }  // namespace
+
+extern "C" int dc_rowdot(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, float* out, dc_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DC_REQUIRE(M >= 0 && N >= 0, DC_EINVAL, "rowdot: negative size");
+  if (M == 0) return DC_OK;
+  DC_REQUIRE(A && B && out && lda >= N && ldb >= N && N < (1ll << 31), DC_EINVAL, "rowdot: bad arguments");
+  rowdot_kernel<<<(unsigned)cdiv(M, 8), 256, 0, st>>>(A, lda, B, ldb, M, (int)N, out);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
 
 extern "C" int dc_softmax_rows(float* S, int64_t ld, int64_t M, int64_t N, dc_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;

@@ -48,7 +48,10 @@ struct alignas(64) T2Problem {
   float* C;
   long long ldc;
   int M, N, kb_total, n_chunks;
-  int pad[8];
+  const float* E;      // optional epilogue operand [M, N] (lde) and row vector [M]:  C = E o (acc - rowv[row])
+  const float* rowv;
+  long long lde;
+  int pad[2];
 };
 
 struct T2Params {
@@ -154,6 +157,8 @@ struct T2Item {
   float* C;
   long long ldc;
   const CUtensorMap *mapA, *mapB;   // batched launches only
+  const float *E, *rowv;            // batched launches only: C = E o (acc - rowv[row])
+  long long lde;
 };
 // work item w of this CTA's sequence (w increases monotonically, so the problem index only moves forward)
 __device__ __forceinline__ T2Item t2_item(const T2Params& p, int w, int& pidx) {
@@ -170,6 +175,7 @@ __device__ __forceinline__ T2Item t2_item(const T2Params& p, int w, int& pidx) {
     it.kb1 = q->kb_total;
     it.M = q->M; it.N = q->N; it.C = q->C; it.ldc = q->ldc;
     it.mapA = &q->mapA; it.mapB = &q->mapB;
+    it.E = q->E; it.rowv = q->rowv; it.lde = q->lde;
     return it;
   }
   it.part = w % p.k_parts;
@@ -180,6 +186,7 @@ __device__ __forceinline__ T2Item t2_item(const T2Params& p, int w, int& pidx) {
   it.kb1 = min(p.kb_total, it.kb0 + p.kb_per_part);
   it.M = p.M; it.N = p.N; it.C = p.C; it.ldc = p.ldc;
   it.mapA = nullptr; it.mapB = nullptr;
+  it.E = nullptr; it.rowv = nullptr; it.lde = 0;
   return it;
 }
 
@@ -390,6 +397,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             if (row < item.M) {
               float4 v = *reinterpret_cast<const float4*>(stg + rr * T2_EPI_ROW + c4);
               v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              if (item.E) {   // fused softmax backward: dS = P o (dP - rowsum(dP o P)), the row sums precomputed as rowdot(dO, O)
+                const float d = item.rowv[row];
+                const float* ep = item.E + (long long)row * item.lde + col;
+                float4 e4;
+                if (((item.lde & 3) == 0) && ((reinterpret_cast<uintptr_t>(item.E) & 15) == 0)) e4 = *reinterpret_cast<const float4*>(ep);
+                else e4 = make_float4(ep[0], ep[1], ep[2], ep[3]);
+                v.x = e4.x * (v.x - d); v.y = e4.y * (v.y - d); v.z = e4.z * (v.z - d); v.w = e4.w * (v.w - d);
+              }
               float4* dst = reinterpret_cast<float4*>(outp + (long long)row * ldo + col);
               if (add_c) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
               if (do_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
@@ -403,6 +418,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             for (int e = 0; e < 4; ++e) {
               if (row < item.M && col + e < item.N) {
                 float v = stg[rr * T2_EPI_ROW + c4 + e] + (bias ? bias[col + e] : 0.f);
+                if (item.E) v = item.E[(long long)row * item.lde + col + e] * (v - item.rowv[row]);
                 float* dst = outp + (long long)row * ldo + col + e;
                 if (add_c) v += *dst;
                 if (do_relu) v = fmaxf(v, 0.f);
@@ -602,6 +618,8 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
       if (int rc = make_map2(&t.mapB, q.B, (uint64_t)q.N, (uint64_t)q.K, (uint64_t)q.ldb, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     }
     t.C = q.C; t.ldc = q.ldc; t.M = (int)q.M; t.N = (int)q.N;
+    t.E = q.E; t.rowv = q.rowv; t.lde = q.lde;
+    DC_REQUIRE(!q.E || (q.rowv && q.lde >= q.N), DC_EINVAL, "gemm_batched: problem %d: epilogue operand needs rowv and lde >= N", i);
     t.kb_total = (int)cdiv(q.K, T2_BK);
     t.n_chunks = (int)cdiv(q.N, T2_BN);
     items += cdiv(q.M, T2_BM) * t.n_chunks;

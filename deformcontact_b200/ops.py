@@ -415,15 +415,18 @@ def gemm(segs, M, N, trans_a=False, trans_b=True, bias=None, relu=False, out=Non
 
 def gemm_batched(problems, trans_a=False, trans_b=True, relu=False, accumulate=False):
     """problems = [(A, B, C), ...]: C_i = act(opA(A_i) opB(B_i)) (+C_i) for all i in one tensor-core launch; see
-    dc_gemm_batched.  Falls back to one dc_gemm per problem when a problem does not fit the tensor path."""
+    dc_gemm_batched.  A problem may carry a fused epilogue (A, B, C, E, rowv): C = E o (acc - rowv[:, None]).
+    Falls back to one dc_gemm per problem when a problem does not fit the tensor path."""
     problems = [q for q in problems if q[2].numel() > 0]
     if not problems:
         return
     arr = (_abi.GemmProblem * len(problems))()
     flops = 0.0
     ok = True
-    for i, (A, B, Cm) in enumerate(problems):
-        _need(A, _f32, "A"), _need(B, _f32, "B"), _need(Cm, _f32, "C")
+    for i, q in enumerate(problems):
+        A, B, Cm = q[:3]
+        E, rowv = (q[3], q[4]) if len(q) > 3 else (None, None)
+        _need(A, _f32, "A"), _need(B, _f32, "B"), _need(Cm, _f32, "C"), _need(E, _f32, "E"), _need(rowv, _f32, "rowv")
         lda, ldb, ldc = _rows(A, "A"), _rows(B, "B"), _rows(Cm, "C")
         K = A.shape[0] if trans_a else A.shape[1]
         Kb = B.shape[1] if trans_b else B.shape[0]
@@ -432,11 +435,15 @@ def gemm_batched(problems, trans_a=False, trans_b=True, relu=False, accumulate=F
         if K != Kb or tuple(Cm.shape) != (M, N):
             raise _abi.DcError(f"gemm_batched: problem {i}: {tuple(A.shape)} x {tuple(B.shape)} -> {tuple(Cm.shape)}")
         ok = ok and K > 0 and lda % 4 == 0 and ldb % 4 == 0 and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0
-        arr[i] = _abi.GemmProblem(A.data_ptr(), lda, B.data_ptr(), ldb, Cm.data_ptr(), ldc, M, N, K)
+        arr[i] = _abi.GemmProblem(A.data_ptr(), lda, B.data_ptr(), ldb, Cm.data_ptr(), ldc, M, N, K, _ptr(E),
+                                  _rows(E, "E") if E is not None else 0, _ptr(rowv))
         flops += 2.0 * M * N * K
     if not ok:
-        for A, B, Cm in problems:
+        for q in problems:
+            A, B, Cm = q[:3]
             gemm([(A, B)], Cm.shape[0], Cm.shape[1], trans_a=trans_a, trans_b=trans_b, relu=relu, out=Cm, accumulate=accumulate)
+            if len(q) > 3:
+                Cm.copy_(q[3] * (Cm - q[4][:, None]))
         return
     nb = _abi.lib().dc_gemm_batched_workspace_bytes(len(problems))
     ws = _workspace(nb, problems[0][0].device)
@@ -444,6 +451,15 @@ def gemm_batched(problems, trans_a=False, trans_b=True, relu=False, accumulate=F
     _abi.call("dc_gemm_batched", arr, len(problems), int(trans_a), int(trans_b), int(bool(relu)), int(bool(accumulate)), _ptr(ws), nb,
               _stream())
     _prof_end(e0, op="gemm", M=0, N=0, K=0, flops=flops)
+
+
+def rowdot(A, B):
+    """out[m] = sum_n A[m, n] * B[m, n]; see dc_rowdot."""
+    _need(A, _f32, "A"), _need(B, _f32, "B")
+    M, N = A.shape
+    out = torch.empty(M, dtype=_f32, device=A.device)
+    _abi.call("dc_rowdot", _ptr(A), _rows(A, "A"), _ptr(B), _rows(B, "B"), M, N, _ptr(out), _stream())
+    return out
 
 
 def colsum(X):

@@ -194,6 +194,9 @@ typedef struct {
   float* C;
   int64_t ldc;
   int64_t M, N, K;
+  const float* E;    /* optional fused epilogue: C = E o (acc - rowv[row]) with E [M, N] (lde), rowv [M]; NULL = none. */
+  int64_t lde;       /* With E = P (attention weights) and rowv = rowdot(dO, O) this is the softmax backward          */
+  const float* rowv; /* dS = P o (dP - rowsum(dP o P)) applied to dP = dO Xr^T as it leaves the tensor core.          */
 } dc_gemm_problem;
 DC_API size_t dc_gemm_batched_workspace_bytes(int32_t count);
 DC_API int dc_gemm_batched(const dc_gemm_problem* problems /*host array*/, int32_t count, int transA, int transB, int relu,
@@ -209,6 +212,9 @@ DC_API int dc_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* o
  * dS[m,n] = P[m,n] * (dP[m,n] - sum_j dP[m,j] P[m,j]).  One CTA per row, fixed reduction tree (deterministic). */
 DC_API int dc_softmax_rows(float* S, int64_t ld, int64_t M, int64_t N, dc_stream_t stream);
 DC_API int dc_softmax_bwd_rows(const float* P, int64_t ldp, float* dP, int64_t ldd, int64_t M, int64_t N, dc_stream_t stream);
+
+/* out[m] = sum_n A[m, n] * B[m, n]  (one warp per row, fixed order) */
+DC_API int dc_rowdot(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, float* out, dc_stream_t stream);
 
 /* dX = dY * (Y > 0)  (backward of the ReLU fused into dc_gemm's epilogue; models/model.py:71,77) */
 DC_API int dc_relu_bwd(const float* Y, const float* dY, float* dX, int64_t numel, dc_stream_t stream);

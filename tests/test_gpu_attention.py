@@ -143,3 +143,22 @@ def test_gemm_batched(dc):
     A = torch.randn(64, 21, generator=g).cuda(); B = torch.randn(32, 21, generator=g).cuda(); Cm = torch.empty(64, 32).cuda()
     ops.gemm_batched([(A, B, Cm)], trans_b=True)
     assert_close(Cm, (A.double() @ B.double().T).float(), what="fallback")
+
+
+def test_gemm_batched_fused_epilogue(dc):
+    """C = E o (A B^T - rowv[:, None]) (the fused softmax backward) and dc_rowdot."""
+    from deformcontact_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    probs, refs = [], []
+    for M, N, K in [(300, 520, 64), (129, 36, 256), (1000, 3048, 32)]:
+        A, B = torch.randn(M, K, generator=g).cuda(), torch.randn(N, K, generator=g).cuda()
+        E = torch.rand((M, (N + 3) // 4 * 4), generator=g).cuda()[:, :N]
+        rv = torch.randn(M, generator=g).cuda()
+        Cm = torch.empty(M, N).cuda()
+        probs.append((A, B, Cm, E, rv))
+        refs.append(E.double() * (A.double() @ B.double().T - rv.double()[:, None]))
+    ops.gemm_batched(probs, trans_b=True)
+    for (A, B, Cm, E, rv), ref in zip(probs, refs):
+        assert_close(Cm, ref.float(), what="fused epilogue")
+    X, Y = torch.randn(777, 100, generator=g).cuda(), torch.randn(777, 100, generator=g).cuda()
+    assert_close(ops.rowdot(X, Y), (X.double() * Y.double()).sum(1).float(), what="rowdot")
