@@ -196,8 +196,7 @@ def run_ours(args):
         pred.pos = pred.pos - rest_b.pos
         tgt = def_b.clone()
         tgt.pos = def_b.pos - rest_b.pos
-        l1 = torch.nn.functional.l1_loss(pred.pos, tgt.pos)
-        lc = dc.GradientConsistencyLoss()(pred, tgt)
+        l1, lc = dc.fused_losses(pred, tgt)   # = F.l1_loss(pred.pos, tgt.pos), GradientConsistencyLoss()(pred, tgt) (train.py:47-58)
         loss = node_share * l1 + edge_share * lc
         loss.backward()
         flat.all_reduce()

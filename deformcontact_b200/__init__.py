@@ -12,6 +12,6 @@ from .data import Data, Batch, collate_fn  # noqa: E402,F401
 from .layers import TAGConv, GCNConv, GATConv, MPNNLayer  # noqa: E402,F401
 from .graph import mesh_to_graph, knn_graph, radius_graph, construct_graph, to_log_freq  # noqa: E402,F401
 from .model import (GraphNet, MultiHeadAttention, GradientConsistencyLoss, load_model,  # noqa: E402,F401
-                    train_step_loss, EVERYDAY)
+                    train_step_loss, fused_losses, EVERYDAY)
 
 __version__ = "0.1.0"

@@ -53,6 +53,7 @@ PROTOTYPES = {
     "dc_gemm_batched": (_int, [C.POINTER(GemmProblem), _i32, _int, _int, _int, _int, _p, _sz, _p]),
     "dc_colsum_workspace_bytes": (_sz, [_i64, _i64]),
     "dc_colsum": (_int, [_p, _i64, _i64, _i64, _p, _p, _sz, _p]),
+    "dc_edge_loss": (_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "dc_rowdot": (_int, [_p, _i64, _p, _i64, _i64, _i64, _p, _p]),
     "dc_softmax_rows": (_int, [_p, _i64, _i64, _i64, _p]),
     "dc_softmax_bwd_rows": (_int, [_p, _i64, _p, _i64, _i64, _i64, _p]),

@@ -156,3 +156,53 @@ extern "C" int dc_softmax_bwd_rows(const float* P, int64_t ldp, float* dP, int64
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// N2 — the training losses of train.py:47-58 in one pass over the CSR pair the encoder already built:
+//   L1 displacement loss   sum_{i,c} |pred[i,c] - tgt[i,c]|                               (nn.L1Loss, train.py:21,52)
+//   gradient consistency   sum_e || (tgt[i]-tgt[j]) - (pred[i]-pred[j]) ||_2, e = (j -> i)  (models/losses.py:12-17)
+// and their gradients with respect to pred, which do not depend on anything upstream but two scalars:
+//   gl[i,c] = sign(pred - tgt),   gc[i] = - sum_{e into i} d_e/|d_e| + sum_{e out of i} d_e/|d_e|   (0 where |d_e| = 0)
+// One thread per node walks its in-edges (by-target CSR) and out-edges (by-source CSR) in CSR order: deterministic, no
+// atomics.  partial[i] = {consistency terms of the edges into i, L1 terms of node i}; the caller sums the columns.
+namespace {
+__global__ void __launch_bounds__(256)
+edge_loss_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr, const int32_t* __restrict__ rowptr_t,
+                 const int32_t* __restrict__ nbr_t, const float* __restrict__ pred, const float* __restrict__ tgt, long long N,
+                 float* __restrict__ partial, float* __restrict__ gc, float* __restrict__ gl) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float px = pred[3 * i], py = pred[3 * i + 1], pz = pred[3 * i + 2];
+  const float tx = tgt[3 * i], ty = tgt[3 * i + 1], tz = tgt[3 * i + 2];
+  const float ex = tx - px, ey = ty - py, ez = tz - pz;   // (tgt - pred)[i]; d_e = e[i] - e[j] for e = (j -> i)
+  float c = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+  for (int p = rowptr[i]; p < rowptr[i + 1]; ++p) {       // edges into i: d = e_i - e_j, dL/dpred_i = -d/|d|
+    const long long j = nbr[p];
+    const float dx = ex - (tgt[3 * j] - pred[3 * j]), dy = ey - (tgt[3 * j + 1] - pred[3 * j + 1]), dz = ez - (tgt[3 * j + 2] - pred[3 * j + 2]);
+    const float n = sqrtf(dx * dx + dy * dy + dz * dz);
+    c += n;
+    if (n > 0.f) { const float r = 1.0f / n; gx -= dx * r; gy -= dy * r; gz -= dz * r; }
+  }
+  for (int p = rowptr_t[i]; p < rowptr_t[i + 1]; ++p) {   // edges out of i (i is the source j of e = (i -> k)): d = e_k - e_i, dL/dpred_i = +d/|d|
+    const long long k = nbr_t[p];
+    const float dx = (tgt[3 * k] - pred[3 * k]) - ex, dy = (tgt[3 * k + 1] - pred[3 * k + 1]) - ey, dz = (tgt[3 * k + 2] - pred[3 * k + 2]) - ez;
+    const float n = sqrtf(dx * dx + dy * dy + dz * dz);
+    if (n > 0.f) { const float r = 1.0f / n; gx += dx * r; gy += dy * r; gz += dz * r; }
+  }
+  partial[2 * i] = c;
+  partial[2 * i + 1] = fabsf(ex) + fabsf(ey) + fabsf(ez);
+  gc[3 * i] = gx; gc[3 * i + 1] = gy; gc[3 * i + 2] = gz;
+  gl[3 * i] = (float)((px > tx) - (px < tx)); gl[3 * i + 1] = (float)((py > ty) - (py < ty)); gl[3 * i + 2] = (float)((pz > tz) - (pz < tz));
+}
+}  // namespace
+
+extern "C" int dc_edge_loss(const int32_t* rowptr, const int32_t* nbr, const int32_t* rowptr_t, const int32_t* nbr_t, const float* pred,
+                            const float* tgt, int64_t N, float* partial, float* gc, float* gl, dc_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DC_REQUIRE(N >= 0, DC_EINVAL, "edge_loss: negative size");
+  if (N == 0) return DC_OK;
+  DC_REQUIRE(rowptr && rowptr_t && pred && tgt && partial && gc && gl, DC_EINVAL, "edge_loss: null pointer");
+  edge_loss_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(rowptr, nbr, rowptr_t, nbr_t, pred, tgt, N, partial, gc, gl);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}

@@ -23,8 +23,9 @@ from . import attention, layers, mlp
 
 # "dcb200": the cross attention runs on libdcb200 (attention.py); "torch": plain fp32 torch / cuBLAS (round-1 path)
 ATTENTION_IMPL = os.environ.get("DCB200_ATTENTION", "dcb200")
-# same switch for the decoder MLP (mlp.py)
+# same switch for the decoder MLP (mlp.py) and the fused training losses (dc_edge_loss)
 DECODER_IMPL = os.environ.get("DCB200_DECODER", "dcb200")
+LOSS_IMPL = os.environ.get("DCB200_LOSS", "dcb200")
 
 EVERYDAY = dict(input_dims=[21, 25], hidden_dim=256, output_dim=3, encoder_layers=2, decoder_layers=3,
                 dropout_rate=0.0, knn_k=7, backbone="TAGConv", use_mha=True, num_mha_heads=2,
@@ -149,6 +150,7 @@ class GraphNet(nn.Module):
         else:
             x_out = self.decoder(torch.cat([x_resting, pooled], dim=-1))
         deformed = graph_resting.clone()
+        deformed._structure_of = graph_resting.edge_index   # same edges: lets fused_losses reuse the encoder's cached CSR pair
         if self.mode == "res":
             deformed.pos = deformed.pos + x_out  # models/model.py:93 (out-of-place: keeps autograd simple)
         elif self.mode == "rec":
@@ -182,12 +184,49 @@ class GradientConsistencyLoss(nn.Module):
         return (er - ep).norm(p=2, dim=-1).sum() / rest.edge_index.shape[1]
 
 
+class _FusedLossFn(torch.autograd.Function):
+    """N2: both losses and their gradients in one pass over the CSR pair of the soft graph (dc_edge_loss)."""
+
+    @staticmethod
+    def forward(ctx, pred_pos, tgt_pos, g):
+        from . import ops, _abi
+        pred_pos, tgt_pos = pred_pos.contiguous(), tgt_pos.contiguous()
+        N = pred_pos.shape[0]
+        partial = torch.empty((N, 2), dtype=torch.float32, device=pred_pos.device)
+        gc, gl = torch.empty_like(pred_pos), torch.empty_like(pred_pos)
+        rp_t, nb_t, _ = g.t
+        _abi.call("dc_edge_loss", ops._ptr(g.rowptr), ops._ptr(g.nbr), ops._ptr(rp_t), ops._ptr(nb_t), ops._ptr(pred_pos),
+                  ops._ptr(tgt_pos), N, ops._ptr(partial), ops._ptr(gc), ops._ptr(gl), ops._stream())
+        sums = ops.colsum(partial)
+        E = max(g.E, 1)
+        ctx.save_for_backward(gc, gl)
+        ctx.scales = (1.0 / (3 * max(N, 1)), 1.0 / E)
+        return sums[1] * ctx.scales[0], sums[0] * ctx.scales[1]
+
+    @staticmethod
+    def backward(ctx, g_l1, g_c):
+        gc, gl = ctx.saved_tensors
+        return gl * (g_l1 * ctx.scales[0]) + gc * (g_c * ctx.scales[1]), None, None
+
+
+def fused_losses(pred, tgt):
+    """(L1 displacement loss, gradient consistency loss) = (F.l1_loss(pred.pos, tgt.pos), GradientConsistencyLoss()(pred, tgt))
+    of train.py:47-58, computed by one libdcb200 kernel on the CSR pair the encoder built for ``pred.edge_index``."""
+    from . import ops
+    ptr = _host_ptr(pred) if getattr(pred, "ptr", None) is not None else None
+    g = ops.graph_csr(getattr(pred, "_structure_of", pred.edge_index), pred.pos.shape[0], "tag", ptr)
+    return _FusedLossFn.apply(pred.pos, tgt.pos, g)
+
+
 def train_step_loss(model, soft_rest, rigid, soft_def, lambda_gradient=1.0):
     """train.py:46-58 without the logging syncs: displacement L1 + lambda * consistency."""
     pred = model(soft_rest, rigid)
     pred.pos = pred.pos - soft_rest.pos
     tgt = soft_def.clone()
     tgt.pos = soft_def.pos - soft_rest.pos
-    loss_l1 = F.l1_loss(pred.pos, tgt.pos)
-    loss_c = GradientConsistencyLoss()(pred, tgt)
+    if LOSS_IMPL == "dcb200" and pred.pos.is_cuda:
+        loss_l1, loss_c = fused_losses(pred, tgt)
+    else:
+        loss_l1 = F.l1_loss(pred.pos, tgt.pos)
+        loss_c = GradientConsistencyLoss()(pred, tgt)
     return loss_l1 + lambda_gradient * loss_c, loss_l1, loss_c

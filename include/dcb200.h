@@ -216,6 +216,15 @@ DC_API int dc_softmax_bwd_rows(const float* P, int64_t ldp, float* dP, int64_t l
 /* out[m] = sum_n A[m, n] * B[m, n]  (one warp per row, fixed order) */
 DC_API int dc_rowdot(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, float* out, dc_stream_t stream);
 
+/* N2 — the two training losses (train.py:47-58: nn.L1Loss on the displacements, models/losses.py:12-17
+ * GradientConsistencyLoss over the edges) and their gradients w.r.t. `pred` in one deterministic pass over the CSR pair
+ * (by target: rowptr / nbr, by source: rowptr_t / nbr_t).  pred, tgt: fp32 [N, 3] contiguous.
+ *   partial [N, 2] = { sum over edges into i of ||(tgt_i - tgt_j) - (pred_i - pred_j)||,  sum_c |pred_ic - tgt_ic| }
+ *   gc [N, 3] = d(sum of edge norms)/d pred_i,   gl [N, 3] = sign(pred - tgt)
+ * The caller sums the columns of `partial` (dc_colsum) and scales by 1/E and 1/(3N). */
+DC_API int dc_edge_loss(const int32_t* rowptr, const int32_t* nbr, const int32_t* rowptr_t, const int32_t* nbr_t, const float* pred,
+                        const float* tgt, int64_t num_nodes, float* partial, float* gc, float* gl, dc_stream_t stream);
+
 /* dX = dY * (Y > 0)  (backward of the ReLU fused into dc_gemm's epilogue; models/model.py:71,77) */
 DC_API int dc_relu_bwd(const float* Y, const float* dY, float* dX, int64_t numel, dc_stream_t stream);
 

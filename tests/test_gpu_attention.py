@@ -162,3 +162,36 @@ def test_gemm_batched_fused_epilogue(dc):
         assert_close(Cm, ref.float(), what="fused epilogue")
     X, Y = torch.randn(777, 100, generator=g).cuda(), torch.randn(777, 100, generator=g).cuda()
     assert_close(ops.rowdot(X, Y), (X.double() * Y.double()).sum(1).float(), what="rowdot")
+
+
+def test_fused_losses(dc):
+    """N2: dc_edge_loss == (F.l1_loss, GradientConsistencyLoss) of train.py:47-58, values and gradients (fp64 arbiter);
+    duplicate edges, self loops (zero-length edge vectors), isolated nodes."""
+    import oracle
+    g = torch.Generator().manual_seed(7)
+    N = 1500
+    ei = torch.randint(0, N - 50, (2, 9000), generator=g)
+    ei = torch.cat([ei, torch.arange(20).repeat(2, 1), ei[:, :100]], 1)      # self loops + duplicates
+    pred_pos = torch.randn(N, 3, generator=g) * 0.01
+    tgt_pos = torch.randn(N, 3, generator=g) * 0.01
+    pred_pos[5] = tgt_pos[5]                                                  # exact zeros in the L1 term
+
+    def run(dtype, dev, fused):
+        p = pred_pos.detach().clone().to(dtype=dtype, device=dev).requires_grad_(True)
+        t = tgt_pos.to(dtype=dtype, device=dev)
+        if fused:
+            a = dc.Data(x=p, edge_index=ei.to(dev), pos=p)
+            b = dc.Data(x=t, edge_index=ei.to(dev), pos=t)
+            l1, lc = dc.fused_losses(a, b)
+        else:
+            a = oracle.Data(x=p, edge_index=ei, pos=p)
+            b = oracle.Data(x=t, edge_index=ei, pos=t)
+            l1, lc = torch.nn.functional.l1_loss(p, t), oracle.GradientConsistencyLoss()(a, b)
+        (0.7 * l1 + 1.3 * lc).backward()
+        return [l1.detach(), lc.detach(), p.grad]
+
+    ours, r32, r64 = run(torch.float32, "cuda", True), run(torch.float32, "cpu", False), run(torch.float64, "cpu", False)
+    for name, a, b32, b64 in zip(("l1", "consistency", "dpred"), ours, r32, r64):
+        assert_close_arbiter(a, b32, b64, what=f"fused loss {name}")
+    again = run(torch.float32, "cuda", True)
+    assert all(torch.equal(x, y) for x, y in zip(ours, again)), "deterministic"
