@@ -7,8 +7,8 @@ Per head (one shared ``nn.Linear`` L for queries and keys, no 1/sqrt(d) scale, v
 Everything runs in libdcb200 through the C ABI: the two projections are one GEMM each over all nodes of the
 batch; inside every attention group (``attn_group`` graphs, see model.py) the score matrix, its softmax and the
 two products with it are ``dc_gemm_batched`` (one launch of the tcgen05 kind::tf32 kernel with the 3-term split per
-product type over ALL groups, fp32-class accuracy) and ``dc_softmax_rows`` / ``dc_softmax_bwd_rows``.  Backward is hand-derived (one ``autograd.Function`` per
-head): dP = dO Xr^T, dXr = P^T dO, dS = P o (dP - rowsum(dP o P)), dQ = dS K, dK = dS^T Q, then the projection
+product type over ALL groups, fp32-class accuracy) and ``dc_softmax_rows`` / ``dc_softmax_bwd_rows``.  Backward is hand-derived (one ``autograd.Function`` over all
+heads): dP = dO Xr^T, dXr = P^T dO, dS = P o (dP - rowsum(dP o P)), dQ = dS K, dK = dS^T Q, then the projection
 gradients over all nodes at once.  The softmax backward is fused into the epilogue of the dP product
 (``rowsum(dP o P) = rowdot(dO, O)``).  The attention weights of a group are kept for backward ([ns, nr] fp32).
 """
@@ -39,61 +39,85 @@ def _groups(ptr_s, ptr_r, group):
     return [(ptr_s[a], ptr_s[min(a + G, B)], ptr_r[a], ptr_r[min(a + G, B)]) for a in range(0, B, G)]
 
 
-class _AttnHeadFn(torch.autograd.Function):
+class _AttnFn(torch.autograd.Function):
+    """All heads at once: every product type is ONE batched launch over heads x groups."""
+
     @staticmethod
-    def forward(ctx, xs, xr, W, b, groups):
+    def forward(ctx, xs, xr, groups, *params):   # params = W_0, b_0, W_1, b_1, ...
         xs, xr = xs.contiguous(), xr.contiguous()
         Ns, F = xs.shape
         Nr = xr.shape[0]
-        q = ops.gemm([(xs, W)], Ns, F, trans_b=True, bias=b)     # L(x_resting)  [Ns, F]
-        k = ops.gemm([(xr, W)], Nr, F, trans_b=True, bias=b)     # L(x_rigid)    [Nr, F]
-        out = torch.empty((Ns, F), dtype=_f32, device=xs.device)
-        live, probs = [], []
+        H = len(params) // 2
+        dev = xs.device
+        live = []
+        outs = [torch.empty((Ns, F), dtype=_f32, device=dev) for _ in range(H)]
         for s0, s1, r0, r1 in groups:
-            ns, nr = s1 - s0, r1 - r0
-            if ns == 0:
+            if s1 - s0 == 0:
                 continue
-            if nr == 0:   # softmax over an empty set: the reference's empty mm gives zeros
-                out[s0:s1].zero_()
+            if r1 - r0 == 0:   # softmax over an empty set: the reference's empty mm gives zeros
+                for o in outs:
+                    o[s0:s1].zero_()
                 continue
             live.append((s0, s1, r0, r1))
-            probs.append(torch.empty((ns, (nr + 3) // 4 * 4), dtype=_f32, device=xs.device)[:, :nr])   # 16-byte aligned rows
-        # one batched tensor-core launch per product type over all groups
-        ops.gemm_batched([(q[s0:s1], k[r0:r1], P) for (s0, s1, r0, r1), P in zip(live, probs)], trans_b=True)       # scores
-        for P in probs:
-            softmax_rows_(P)
-        ops.gemm_batched([(P, xr[r0:r1], out[s0:s1]) for (s0, s1, r0, r1), P in zip(live, probs)], trans_b=False)   # attn @ x_rigid
-        ctx.save_for_backward(xs, xr, W, q, k, out)
-        ctx.probs, ctx.groups = probs, live
-        return out
+        qs, ks, probs = [], [], []
+        for h in range(H):
+            W, b = params[2 * h], params[2 * h + 1]
+            qs.append(ops.gemm([(xs, W)], Ns, F, trans_b=True, bias=b))     # L_h(x_resting)  [Ns, F]
+            ks.append(ops.gemm([(xr, W)], Nr, F, trans_b=True, bias=b))     # L_h(x_rigid)    [Nr, F]
+            probs.append([torch.empty((s1 - s0, (r1 - r0 + 3) // 4 * 4), dtype=_f32, device=dev)[:, :r1 - r0]   # 16-byte aligned rows
+                          for s0, s1, r0, r1 in live])
+        HG = [(h, i, g) for h in range(H) for i, g in enumerate(live)]
+        ops.gemm_batched([(qs[h][s0:s1], ks[h][r0:r1], probs[h][i]) for h, i, (s0, s1, r0, r1) in HG], trans_b=True)      # scores
+        for h in range(H):
+            for P in probs[h]:
+                softmax_rows_(P)
+        ops.gemm_batched([(probs[h][i], xr[r0:r1], outs[h][s0:s1]) for h, i, (s0, s1, r0, r1) in HG], trans_b=False)      # attn @ x_rigid
+        ctx.save_for_backward(xs, xr, *params, *qs, *ks, *outs)
+        ctx.probs, ctx.groups, ctx.H = probs, live, H
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, dout):
-        xs, xr, W, q, k, out = ctx.saved_tensors
-        dout = dout.contiguous()
+    def backward(ctx, *douts):
+        H, live, probs = ctx.H, ctx.groups, ctx.probs
+        saved = ctx.saved_tensors
+        xs, xr = saved[0], saved[1]
+        params = saved[2:2 + 2 * H]
+        qs, ks, outs = saved[2 + 2 * H:2 + 3 * H], saved[2 + 3 * H:2 + 4 * H], saved[2 + 4 * H:2 + 5 * H]
         Ns, F = xs.shape
         Nr = xr.shape[0]
-        groups, probs = ctx.groups, ctx.probs
-        dq = torch.zeros((Ns, F), dtype=_f32, device=xs.device)
-        dk = torch.zeros((Nr, F), dtype=_f32, device=xs.device)
-        dxr = torch.zeros((Nr, F), dtype=_f32, device=xs.device)
-        dPs = [torch.empty((P.shape[0], P.stride(0)), dtype=_f32, device=xs.device)[:, :P.shape[1]] for P in probs]
-        G = list(zip(groups, probs, dPs))
+        dev = xs.device
+        douts = [d.contiguous() for d in douts]
+        dq = [torch.zeros((Ns, F), dtype=_f32, device=dev) for _ in range(H)]
+        dk = [torch.zeros((Nr, F), dtype=_f32, device=dev) for _ in range(H)]
+        dxr_h = [torch.zeros((Nr, F), dtype=_f32, device=dev) for _ in range(H)]
+        dPs = [[torch.empty((P.shape[0], P.stride(0)), dtype=_f32, device=dev)[:, :P.shape[1]] for P in probs[h]] for h in range(H)]
+        HG = [(h, i, g) for h in range(H) for i, g in enumerate(live)]
         # softmax backward dS = P o (dP - rowsum(dP o P)) fused into the epilogue of dP = dO Xr^T: the row sums equal
         # rowdot(dO, O) because O = P Xr, so they are known before the product starts
-        D = ops.rowdot(dout, out)
-        ops.gemm_batched([(dout[s0:s1], xr[r0:r1], dP, P, D[s0:s1]) for (s0, s1, r0, r1), P, dP in G], trans_b=True)          # dS
-        ops.gemm_batched([(P, dout[s0:s1], dxr[r0:r1]) for (s0, s1, r0, r1), P, dP in G], trans_a=True, trans_b=False)       # dXr = P^T dO
-        ops.gemm_batched([(dP, k[r0:r1], dq[s0:s1]) for (s0, s1, r0, r1), P, dP in G], trans_b=False)                         # dQ = dS K
-        ops.gemm_batched([(dP, q[s0:s1], dk[r0:r1]) for (s0, s1, r0, r1), P, dP in G], trans_a=True, trans_b=False)           # dK = dS^T Q
+        D = [ops.rowdot(douts[h], outs[h]) for h in range(H)]
+        ops.gemm_batched([(douts[h][s0:s1], xr[r0:r1], dPs[h][i], probs[h][i], D[h][s0:s1]) for h, i, (s0, s1, r0, r1) in HG],
+                         trans_b=True)                                                                                   # dS
+        ops.gemm_batched([(probs[h][i], douts[h][s0:s1], dxr_h[h][r0:r1]) for h, i, (s0, s1, r0, r1) in HG],
+                         trans_a=True, trans_b=False)                                                                    # dXr_h = P^T dO
+        ops.gemm_batched([(dPs[h][i], ks[h][r0:r1], dq[h][s0:s1]) for h, i, (s0, s1, r0, r1) in HG], trans_b=False)      # dQ = dS K
+        ops.gemm_batched([(dPs[h][i], qs[h][s0:s1], dk[h][r0:r1]) for h, i, (s0, s1, r0, r1) in HG],
+                         trans_a=True, trans_b=False)                                                                    # dK = dS^T Q
         ctx.probs = None
         # projections: q = xs W^T + b, k = xr W^T + b
-        dxs = ops.gemm([(dq, W)], Ns, F, trans_b=False)
-        ops.gemm([(dk, W)], Nr, F, trans_b=False, out=dxr, accumulate=True)
-        dW = ops.gemm([(dq, xs)], F, F, trans_a=True, trans_b=False)
-        ops.gemm([(dk, xr)], F, F, trans_a=True, trans_b=False, out=dW, accumulate=True)
-        db = ops.colsum(dq) + ops.colsum(dk)
-        return dxs, dxr, dW, db, None
+        dxs, dxr, grads = None, None, []
+        for h in range(H):
+            W = params[2 * h]
+            if dxs is None:
+                dxs = ops.gemm([(dq[h], W)], Ns, F, trans_b=False)
+                dxr = dxr_h[h]
+            else:
+                ops.gemm([(dq[h], W)], Ns, F, trans_b=False, out=dxs, accumulate=True)
+                dxr = dxr + dxr_h[h]
+            ops.gemm([(dk[h], W)], Nr, F, trans_b=False, out=dxr, accumulate=True)
+            dW = ops.gemm([(dq[h], xs)], F, F, trans_a=True, trans_b=False)
+            ops.gemm([(dk[h], xr)], F, F, trans_a=True, trans_b=False, out=dW, accumulate=True)
+            grads += [dW, ops.colsum(dq[h]) + ops.colsum(dk[h])]
+        return (dxs, dxr, None, *grads)
 
 
 def cross_attention(x_resting, x_rigid, heads, ptr_s, ptr_r, group=None, concat=True):
@@ -101,5 +125,8 @@ def cross_attention(x_resting, x_rigid, heads, ptr_s, ptr_r, group=None, concat=
     (models/model.py:14-21), or as a list when ``concat`` is False (the decoder consumes them as GEMM K-segments).
     ``ptr_s`` / ``ptr_r``: host lists of graph offsets of the two batches."""
     groups = _groups(ptr_s, ptr_r, group)
-    outs = [_AttnHeadFn.apply(x_resting, x_rigid, h.weight, h.bias, groups) for h in heads]
+    params = []
+    for h in heads:
+        params += [h.weight, h.bias]
+    outs = list(_AttnFn.apply(x_resting, x_rigid, groups, *params))
     return torch.cat(outs, dim=-1) if concat else outs

@@ -40,7 +40,7 @@ constexpr int T2_EPI_ROW = 20;                                // staging row: 16
 constexpr int T2_EPI_WARP_FLOATS = 32 * T2_EPI_ROW;
 constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOATS * 4 + 256 + 1024;
 constexpr int T2_DRAIN_KB = 8;                                // chain length in k-blocks (32 MMA steps)
-constexpr int T2_MAX_KPARTS = 16;
+constexpr int T2_MAX_KPARTS = 64;   // weight gradients: 256 x 256 outputs over 512k nodes need ~37 parts to fill 148 SMs
 
 // one problem of a batched launch (device table; the tensor maps are read by TMA straight from global memory)
 struct alignas(64) T2Problem {

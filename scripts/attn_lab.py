@@ -14,7 +14,7 @@ b = ((torch.rand(F, generator=g, device=dev) * 2 - 1) / 16).requires_grad_(True)
 go = torch.randn(ns * G, F, generator=g, device=dev)
 groups = [(i * ns, (i + 1) * ns, i * nr, (i + 1) * nr) for i in range(G)]
 def step():
-    out = attention._AttnHeadFn.apply(xs, xr, W, b, groups)
+    out = attention._AttnFn.apply(xs, xr, groups, W, b)[0]
     out.backward(go)
 for _ in range(2): step()
 torch.cuda.synchronize()

@@ -9,6 +9,8 @@ shapes = [  # M, N, K, trans_a, trans_b, label
     (512000, 256, 1024, False, True, "layer fwd"),
     (512000, 1024, 256, False, False, "layer dX"),
     (256, 1024, 512000, True, False, "layer dW"),
+    (256, 256, 512000, True, False, "dW 1 hop"),
+    (256, 24, 512000, True, False, "dW layer1"),
     (8000, 3048, 256, False, True, "scores"),
     (8000, 256, 3048, False, False, "attn @ Xr"),
     (3048, 256, 8000, True, False, "P^T dO"),

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.txt
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python scripts/gemm_lab.py 2>&1 | tail -8
 timeout 600 python bench.py --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_default.json
 python -c "
 import json

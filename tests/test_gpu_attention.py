@@ -43,7 +43,7 @@ def test_cross_attention_forward_backward(dc, F, ptr_s, ptr_r, group):
     def run(dtype, dev):
         t = [v.detach().clone().to(dtype=dtype, device=dev).requires_grad_(True) for v in (xs, xr, W, b)]
         if dev == "cuda":
-            out = attention._AttnHeadFn.apply(*t, groups)
+            out = attention._AttnFn.apply(t[0], t[1], groups, t[2], t[3])[0]
         else:
             out = _ref(*t, groups)
         out.backward(go.to(dtype=dtype, device=dev))
