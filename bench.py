@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--cpu-sample-graphs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-inputs", choices=["raw", "collated"], default="raw",
+                    help="end-to-end arm: 'raw' = positions + graph-local edges + collider parameters, batch assembled on the GPU "
+                         "(N3); 'collated' = host-built batches (features, offset edges) copied as they are")
     ap.add_argument("--layer", default="tag", choices=["tag", "gcn", "gat", "mpnn"], help="C5: which layer")
     ap.add_argument("--no-tiles", action="store_true", help="C5: fixed 2048-node tiles instead of graph-aligned tiles")
     ap.add_argument("--hidden", type=int, default=256, help="C5 sweep: feature width")
@@ -282,20 +285,46 @@ def run_ours(args):
     E_local = rest.edge_index.shape[1] + rigid.edge_index.shape[1]
     extra["edge_traversals_per_sec"] = (2 * 3 * 2) * E_local * world / (ms_step * 1e-3)  # 2 layers x 3 hops x (fwd+bwd)
 
-    # ---- end-to-end arm: pinned host inputs -> H2D -> step -> D2H loss
+    # ---- end-to-end arm: pinned host inputs -> H2D -> (N3 batch assembly on the GPU) -> step -> D2H loss
     e2e = None
     if not args.no_e2e:
-        host = {k: v.cpu().pin_memory() for k, v in dict(rx=rest.x, rp=rest.pos, dp=deformed.pos, re=rest.edge_index,
-                                                         gx=rigid.x, gp=rigid.pos, ge=rigid.edge_index, rptr=rest.ptr,
-                                                         gptr=rigid.ptr).items()}
-        h2d = sum(v.numel() * v.element_size() for v in host.values())
         loss_host = torch.zeros(1).pin_memory()
+        if args.e2e_inputs == "collated":
+            # the batches exactly as the reference's host-side from_data_list leaves them (features and offset edges built on the host)
+            host = {k: v.cpu().pin_memory() for k, v in dict(rx=rest.x, rp=rest.pos, dp=deformed.pos, re=rest.edge_index,
+                                                             gx=rigid.x, gp=rigid.pos, ge=rigid.edge_index, rptr=rest.ptr,
+                                                             gptr=rigid.ptr).items()}
+
+            def assemble_step():
+                d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+                rb = dc.Batch(x=d["rx"], edge_index=d["re"], pos=d["rp"]); rb.ptr = d["rptr"]; rb._ptr_host = rest._ptr_host
+                db = dc.Batch(x=d["rx"], edge_index=d["re"], pos=d["dp"]); db.ptr = d["rptr"]
+                gb = dc.Batch(x=d["gx"], edge_index=d["ge"], pos=d["gp"]); gb.ptr = d["gptr"]; gb._ptr_host = rigid._ptr_host
+                return rb, gb, db
+        else:
+            # raw per-sample inputs, packed by the loader: positions, graph-local edge lists, collider contact point + force;
+            # features, index offsets, batch vectors, collider spheres and their mesh edges are produced on the GPU (N3)
+            eptr = torch.tensor(rest._edge_ptr if rest._edge_ptr is not None else
+                                [0] + torch.bincount(rest.batch[rest.edge_index[1]], minlength=Bg).cumsum(0).tolist(), dtype=torch.long)
+            local = rest.edge_index - rest.ptr[:-1][rest.batch[rest.edge_index[1]]]
+            host = {"rp": rest.pos, "dp": deformed.pos, "le": local, "nptr": rest.ptr, "eptr": eptr,
+                    "centers": rigid._centers, "fvec": rigid._head[:, 0:3], "force": rigid._head[:, 3]}
+            host = {k: v.cpu().contiguous().pin_memory() for k, v in host.items()}
+
+            def assemble_step():
+                rb = dc.graph_batch_packed(host["rp"], host["le"], host["nptr"], host["eptr"], device=dev)
+                db = dc.Batch(x=rb.x, edge_index=rb.edge_index, pos=host["dp"].to(dev, non_blocking=True)); db.ptr = rb.ptr
+                gb = dc.collider_batch(host["centers"], host["fvec"], host["force"], device=dev)
+                return rb, gb, db
+
+            rb, gb, _ = assemble_step()   # the assembled batches are the device-resident ones (indices and positions bit for bit)
+            assert torch.equal(rb.edge_index, rest.edge_index) and torch.equal(rb.pos, rest.pos), "N3 soft batch differs"
+            assert torch.equal(gb.edge_index, rigid.edge_index) and torch.equal(gb.pos, rigid.pos), "N3 collider batch differs"
+            assert (rb.x - rest.x).abs().max().item() <= 1e-6 and (gb.x - rigid.x).abs().max().item() <= 1e-6, "N3 features differ"
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
 
         def e2e_step():
-            d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-            rb = dc.Batch(x=d["rx"], edge_index=d["re"], pos=d["rp"]); rb.ptr = d["rptr"]; rb._ptr_host = rest._ptr_host
-            db = dc.Batch(x=d["rx"], edge_index=d["re"], pos=d["dp"]); db.ptr = d["rptr"]
-            gb = dc.Batch(x=d["gx"], edge_index=d["ge"], pos=d["gp"]); gb.ptr = d["gptr"]; gb._ptr_host = rigid._ptr_host
+            rb, gb, db = assemble_step()
             loss = step(rb, gb, db)
             loss_host.copy_(loss.detach().reshape(1), non_blocking=False)   # D2H read of the step's result
 
@@ -303,7 +332,7 @@ def run_ours(args):
             e2e_step()
         e2e_ms = timed(e2e_step, args.steps) / args.steps
         e2e = {"value": Bg * world / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "inputs": args.e2e_inputs}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -64,6 +64,11 @@ PROTOTYPES = {
     "dc_nbr_to_edge_index": (_int, [_p, _i64, _i32, _p, _i64, _p, _p, _sz, _p]),
     "dc_mesh_edges": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p]),
     "dc_posenc": (_int, [_p, _i64, _p, _i64, _i32, _p]),
+    "dc_batch_vector": (_int, [_p, _i64, _i64, _p, _p]),
+    "dc_edges_offset": (_int, [_p, _i32, _i64, _p, _p, _i64, _i64, _p, _i64, _p]),
+    "dc_mesh_edges_batched": (_int, [_p, _i32, _p, _p, _i64, _i64, _i64, _i64, _p, _i64, _p]),
+    "dc_node_features": (_int, [_p, _p, _i32, _p, _i64, _i64, _p, _i64, _p]),
+    "dc_instance_points": (_int, [_p, _p, _i64, _i64, _p, _p]),
     "dc_gat_scores": (_int, [_p, _i64, _i64, _i32, _i32, _p, _p, _p, _p, _p]),
     "dc_gat_softmax": (_int, [_p, _p, _p, _p, _p, _f32, _i64, _p, _p, _p]),
     "dc_gat_bwd_edge": (_int, [_p, _p, _p, _p, _p, _f32, _p, _p, _p, _i64, _p, _i64, _i32, _i64, _p, _p, _p, _p]),

@@ -55,7 +55,12 @@ class Data:
 
 class Batch(Data):
     @classmethod
-    def from_data_list(cls, data_list):
+    def from_data_list(cls, data_list, device=None):
+        """PyG layout (data/batch.py).  With ``device`` a CUDA device and CPU inputs, the batch is assembled on the
+        GPU from one packed copy (``assemble.batch_from_data_list`` = ``from_data_list(...).to(device)``)."""
+        if device is not None and torch.device(device).type == "cuda":
+            from .assemble import batch_from_data_list
+            return batch_from_data_list(data_list, device=device)
         sizes = [d.num_nodes for d in data_list]
         esizes = [d.num_edges for d in data_list]
         ref = next((t for d in data_list for t in (d.x, d.pos, d.edge_index) if t is not None), None)

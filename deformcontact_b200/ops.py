@@ -550,6 +550,82 @@ def posenc(pos, out=None, col0=0):
     return out
 
 
+# ----------------------------------------------------------------------------- N3: batch assembly
+def _index_bytes(t, name):
+    if t.dtype == _i32:
+        return 4
+    if t.dtype == _i64:
+        return 8
+    raise _abi.DcError(f"{name}: expected int32 or int64 indices, got {t.dtype}")
+
+
+def batch_vector(node_ptr, num_nodes):
+    """Batch.batch: int64 [N] graph id per node from ``ptr`` (int64 [B+1], device)."""
+    _need(node_ptr, _i64, "node_ptr")
+    out = torch.empty(int(num_nodes), dtype=_i64, device=node_ptr.device)
+    _abi.call("dc_batch_vector", _ptr(node_ptr), node_ptr.numel() - 1, int(num_nodes), _ptr(out), _stream())
+    return out
+
+
+def edges_offset(local, edge_ptr, node_ptr, out=None):
+    """``local`` [2, E] graph-local indices (int32 / int64), graphs back to back -> int64 [2, E] with each graph's
+    cumulative node offset added (the ``edge_index`` increment of PyG's collate)."""
+    _need(edge_ptr, _i64, "edge_ptr"); _need(node_ptr, _i64, "node_ptr")
+    if not local.is_cuda:
+        raise _abi.DcError("local: expected a CUDA tensor (libdcb200 has no CPU path)")
+    ib = _index_bytes(local, "local")
+    E = local.shape[1]
+    if out is None:
+        out = torch.empty((2, E), dtype=_i64, device=local.device)
+    _abi.call("dc_edges_offset", _ptr(local), ib, _rows(local, "local"), _ptr(edge_ptr), _ptr(node_ptr), node_ptr.numel() - 1, E,
+              _ptr(out), _rows(out, "out"), _stream())
+    return out
+
+
+def mesh_edges_batched(triangles, tri_ptr=None, node_ptr=None, num_graphs=None, nodes_per_graph=0, out=None):
+    """mesh_to_graph edges of a whole batch in one launch.  Ragged: ``triangles`` [sum T, 3] local indices with
+    ``tri_ptr`` / ``node_ptr``.  Instanced (``tri_ptr`` None): ``triangles`` [T, 3] is a template shared by
+    ``num_graphs`` graphs of ``nodes_per_graph`` nodes each."""
+    if not triangles.is_cuda:
+        raise _abi.DcError("triangles: expected a CUDA tensor (libdcb200 has no CPU path)")
+    ib = _index_bytes(triangles, "triangles")
+    tri = triangles.contiguous()
+    if tri_ptr is not None:
+        _need(tri_ptr, _i64, "tri_ptr"); _need(node_ptr, _i64, "node_ptr")
+        B, T, tpg = node_ptr.numel() - 1, tri.shape[0], 0
+    else:
+        B, tpg = int(num_graphs), tri.shape[0]
+        T = B * tpg
+    if out is None:
+        out = torch.empty((2, 3 * T), dtype=_i64, device=tri.device)
+    _abi.call("dc_mesh_edges_batched", _ptr(tri), ib, _ptr(tri_ptr), _ptr(node_ptr), B, T, tpg, int(nodes_per_graph), _ptr(out),
+              _rows(out, "out"), _stream())
+    return out
+
+
+def node_features(pos, head=None, node_ptr=None, out=None):
+    """[head[graph(n)] | to_log_freq(pos[n], 3, 1)]: the 21-d soft features (``head`` None) or the collider's
+    25-d ``_feature_rigid`` (``head`` fp32 [B, 4] = force_vector | force)."""
+    _need(pos, _f32, "pos"); _need(head, _f32, "head"); _need(node_ptr, _i64, "node_ptr")
+    pos = pos.contiguous()
+    N = pos.shape[0]
+    H = 0 if head is None else head.shape[1]
+    if out is None:
+        out = torch.empty((N, H + 21), dtype=_f32, device=pos.device)
+    _abi.call("dc_node_features", _ptr(pos), _ptr(None if head is None else head.contiguous()), H, _ptr(node_ptr),
+              0 if node_ptr is None else node_ptr.numel() - 1, N, _ptr(out), _rows(out, "out"), _stream())
+    return out
+
+
+def instance_points(template, centers):
+    """fp64 template [V, 3] + fp64 centers [B, 3] -> fp32 [B*V, 3] (fp64 add, then round: Open3D translate)."""
+    _need(template, torch.float64, "template"); _need(centers, torch.float64, "centers")
+    B, V = centers.shape[0], template.shape[0]
+    out = torch.empty((B * V, 3), dtype=_f32, device=template.device)
+    _abi.call("dc_instance_points", _ptr(template.contiguous()), _ptr(centers.contiguous()), B, V, _ptr(out), _stream())
+    return out
+
+
 # ----------------------------------------------------------------------------- K6
 def gat_scores(xs, att_src, att_dst, heads, C_):
     N = xs.shape[0]

@@ -48,7 +48,7 @@ def make_batch(n_graphs, n_nodes=2000, k=8, first=0, device="cuda"):
     """-> (soft_rest, rigid, soft_deformed) ``Batch``es on ``device`` (graphs first..first+n_graphs-1)."""
     sv, st = uv_sphere()
     nv = sv.shape[0]
-    pos_l, def_l, rpos_l, rhead_l = [], [], [], []
+    pos_l, def_l, rpos_l, rhead_l, centers, heads = [], [], [], [], [], []
     for g in range(first, first + n_graphs):
         gen = torch.Generator().manual_seed(1234 + g)
         pos = torch.rand(n_nodes, 3, generator=gen) - 0.5
@@ -61,6 +61,8 @@ def make_batch(n_graphs, n_nodes=2000, k=8, first=0, device="cuda"):
         def_l.append(dpos)
         rpos_l.append((sv + pos[ci].double()).float())
         rhead_l.append(torch.cat([fdir, force]).repeat(nv, 1))
+        centers.append(pos[ci].double())
+        heads.append(torch.cat([fdir, force]))
     pos = torch.cat(pos_l).to(device)
     dpos = torch.cat(def_l).to(device)
     rpos = torch.cat(rpos_l).to(device)
@@ -88,4 +90,6 @@ def make_batch(n_graphs, n_nodes=2000, k=8, first=0, device="cuda"):
     rest = batch(x, ei, pos, ptr, n_nodes, e_per)
     deformed = batch(x, ei, dpos, ptr, n_nodes, e_per)
     rigid = batch(rx, rei, rpos, rptr, nv, 3 * tri.shape[0])
+    # the raw per-sample collider parameters (contact point, force direction | magnitude): what assemble.collider_batch takes
+    rigid._centers, rigid._head = torch.stack(centers), torch.stack(heads)
     return rest, rigid, deformed

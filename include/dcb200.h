@@ -259,6 +259,36 @@ DC_API int dc_mesh_edges(const int64_t* triangles, int64_t num_tri, int64_t offs
 /* to_log_freq(pos, 3, 1) (utils/pos_encoding.py:6-44): [N,3] -> [N,21] at out[:, col0:col0+21]. */
 DC_API int dc_posenc(const float* pos, int64_t num_points, float* out, int64_t ldo, int32_t col0, dc_stream_t stream);
 
+/* ---------------------------------------------------------------- N3: on-GPU batch assembly
+ * Replaces Batch.from_data_list(...).to(device) (train.py:36-44; PyG data/batch.py), the per-sample
+ * mesh_to_graph loop (utils/graph_utils.py:12-16), _feature_rigid (loaders/common.py:6-19) and the
+ * collider sphere instancing (loaders/common.py:25-30).  The host concatenates the per-sample arrays
+ * with GRAPH-LOCAL indices into one staging buffer and copies it once; these kernels emit the batched
+ * layout.  `node_ptr`, `edge_ptr`, `tri_ptr`: int64 [B+1] device arrays of cumulative counts
+ * (ptr[0] = 0; empty graphs allowed).  `index_bytes` = 4 (int32) or 8 (int64) for local indices. */
+/* batch[i] = graph of node i (Batch.batch), int64 [N]. */
+DC_API int dc_batch_vector(const int64_t* node_ptr, int64_t num_graphs, int64_t num_nodes, int64_t* batch,
+                    dc_stream_t stream);
+/* edge_index[:, e] = local[:, e] + node_ptr[graph of edge e]; local is [2, E] with row stride
+ * `local_stride` elements, edge_index int64 [2, E] with row stride `edge_stride`. */
+DC_API int dc_edges_offset(const void* local, int32_t index_bytes, int64_t local_stride, const int64_t* edge_ptr,
+                    const int64_t* node_ptr, int64_t num_graphs, int64_t num_edges, int64_t* edge_index,
+                    int64_t edge_stride, dc_stream_t stream);
+/* mesh_to_graph half-edges (a,b),(b,c),(c,a) for every graph of a batch in one launch.
+ * Ragged form: triangles [num_tri, 3] local indices, tri_ptr / node_ptr given.
+ * Instanced form (tri_ptr = NULL): the same `tri_per_graph` template triangles for each of the
+ * num_graphs graphs, graph g offset by g * nodes_per_graph; num_tri = num_graphs * tri_per_graph. */
+DC_API int dc_mesh_edges_batched(const void* triangles, int32_t index_bytes, const int64_t* tri_ptr,
+                          const int64_t* node_ptr, int64_t num_graphs, int64_t num_tri, int64_t tri_per_graph,
+                          int64_t nodes_per_graph, int64_t* edge_index, int64_t edge_stride, dc_stream_t stream);
+/* out[n, :] = [head[graph(n), 0:head_width] | to_log_freq(pos[n], 3, 1)]  (head_width = 0: the 21-d soft
+ * features; head_width = 4: the collider's [force_vector | force] ++ posenc, loaders/common.py:18). */
+DC_API int dc_node_features(const float* pos, const float* head, int32_t head_width, const int64_t* node_ptr,
+                     int64_t num_graphs, int64_t num_nodes, float* out, int64_t ldo, dc_stream_t stream);
+/* pos[g*V + v, :] = float(tmpl[v, :] + centers[g, :]) with the add in fp64 (Open3D translate). */
+DC_API int dc_instance_points(const double* tmpl, const double* centers, int64_t num_graphs, int64_t num_template_points,
+                       float* pos, dc_stream_t stream);
+
 /* ---------------------------------------------------------------- K6: GAT attention pieces
  * (PyG nn/conv/gat_conv.py, utils/softmax.py)  a_src[n,h] = sum_c xs[n,h,c]*att_src[h,c] etc. */
 DC_API int dc_gat_scores(const float* xs, int64_t ld, int64_t num_nodes, int32_t heads, int32_t C, const float* att_src,

@@ -17,6 +17,25 @@ def _g(seed=0, n=200, e=1500):
 
 
 # ---------------------------------------------------------------- pinned against the reference's own code
+def test_assemble_golden(golden_dir):
+    """The oracle's mesh_to_graph / _feature_rigid / from_data_list restatement against the fixture produced by the
+    reference's own utils/graph_utils.py:mesh_to_graph and loaders/common.py:_feature_rigid (make_golden_assemble.py)."""
+    gold = torch.load(f"{golden_dir}/assemble.pt")
+    soft = oracle.Batch.from_data_list([oracle.mesh_to_graph(v, t.long()) for v, t in gold["meshes"]])
+    for k in ("x", "pos", "edge_index", "batch", "ptr"):
+        assert torch.equal(getattr(soft, k), gold["soft"][k]), k
+    sv, st = oracle.uv_sphere(0.05, 20)
+    rigid = []
+    for c, fv, f in zip(gold["centers"], gold["force_vec"], gold["force"]):
+        d = oracle.mesh_to_graph(sv + c, st)
+        n = d.x.shape[0]
+        d.x = torch.cat([fv.repeat(n, 1), f.float().reshape(1).repeat(n, 1), d.x], dim=1)
+        rigid.append(d)
+    rb = oracle.Batch.from_data_list(rigid)
+    for k in ("x", "pos", "edge_index", "batch", "ptr"):
+        assert torch.equal(getattr(rb, k), gold["rigid"][k]), k
+
+
 def test_posenc_golden(golden_dir):
     gold = torch.load(f"{golden_dir}/posenc.pt")
     assert torch.equal(oracle.to_log_freq(gold["pos"], 3, 1), gold["out"])
