@@ -248,13 +248,13 @@ def run_ours(args):
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     hop_bytes = hop_ms = 0.0
-    hop_n = 0
+    hop_n = hop_hops = 0
     gemm_flops = gemm_ms = 0.0
     other = {}
     for rec in prof:
         ms = rec["e0"].elapsed_time(rec["e1"])
         if rec["op"] == "spmm" and rec["F"] == 256:
-            hop_bytes += rec["bytes"]; hop_ms += ms; hop_n += 1
+            hop_bytes += rec["bytes"]; hop_ms += ms; hop_n += 1; hop_hops += rec.get("hops", 1)
         elif rec["op"] == "gemm":
             gemm_flops += rec["flops"]; gemm_ms += ms
         other[rec["op"]] = other.get(rec["op"], 0.0) + ms
@@ -264,11 +264,13 @@ def run_ours(args):
         roofline = {"kernel": f"K1 gather/segmented-sum hop, F=256 ({ops.K1_VARIANT} variant)", "bound": "hbm",
                     "achieved": ach, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / hbm_peak,
                     "traffic": K1_NCU_TRAFFIC_RATIO * hop_bytes / hop_n, "traffic_source": K1_NCU_TRAFFIC_SOURCE,
-                    "launches": hop_n // args.steps, "avg_launch_ms": hop_ms / hop_n,
+                    "launches": hop_n // args.steps, "hops": hop_hops // args.steps, "avg_launch_ms": hop_ms / hop_n,
+                    "avg_hop_ms": hop_ms / hop_hops,
                     "algorithmic_bytes_per_launch": hop_bytes / hop_n,
                     "share_of_step": hop_ms / total_ms,
-                    "note": "bytes = 8NF+4E+8N+4 per hop (+4NF when a fused addend is read); timed with CUDA events "
-                            "around each launch inside the timed steps"}
+                    "note": "bytes = 8NF+4E+8N+4 per hop (+4NF when a fused addend is read), summed over the hops of a chain "
+                            "launch (K1 v9: the 3 hops of a TAGConv layer in one launch); timed with CUDA events around each "
+                            "launch inside the timed steps"}
     extra = {"our_kernel_ms_per_step": {k: v / args.steps for k, v in other.items()}}
     if gemm_ms:
         tf = gemm_flops / (gemm_ms * 1e-3) / 1e12

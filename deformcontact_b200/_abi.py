@@ -27,6 +27,13 @@ class GemmProblem(C.Structure):
                 ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("E", C.c_void_p), ("lde", C.c_int64), ("rowv", C.c_void_p)]
 
 
+class Hop(C.Structure):
+    _fields_ = [("inp", C.c_void_p), ("ldin", C.c_int64), ("add", C.c_void_p), ("ldadd", C.c_int64), ("out", C.c_void_p),
+                ("ldout", C.c_int64)]
+
+
+MAX_CHAIN = 4
+
 _p, _i64, _i32, _f32, _sz, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t, C.c_int
 
 # name -> (restype, argtypes); mirrors include/dcb200.h one to one
@@ -42,6 +49,7 @@ PROTOTYPES = {
     "dc_spmm_tiled": (_int, [_p, _p, _p, _p, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _int, _p, _int, _p, _i64, _i32, _int, _p]),
     "dc_pack_edges": (_int, [_p, _p, _i64, _p, _p]),
     "dc_spmm_lean": (_int, [_p, _p, _p, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _int, _p, _int, _p, _i64, _i32, _p]),
+    "dc_spmm_chain": (_int, [_p, _p, _p, C.POINTER(Hop), _i32, _i64, _i32, _int, _p, _i64, _i32, _p]),
     "dc_blocks_workspace_bytes": (_sz, [_i64]),
     "dc_blocks_record_capacity": (_i64, [_i64, _i64, _i64]),
     "dc_blocks_build": (_int, [_p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _i64, _p, _p, _p, _sz, _p]),

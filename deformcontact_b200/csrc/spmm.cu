@@ -599,6 +599,89 @@ spmm_lean_kernel(const int32_t* __restrict__ rowptr, const int2* __restrict__ ed
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K1 v9 — hop CHAIN: the consecutive hops of one layer (TAGConv forward h_{k+1} = A h_k, k = 0..K-1, and the
+// backward chain g_{k-1} = dH_{k-1} + A^T g_k) in ONE launch.  Same tile x 128-byte-slice mapping and inner loop
+// as the lean kernel, but the CTA keeps its (tile, slice) and walks all hops with a block barrier in between.
+// That is legal because hops are column-wise independent (column c of hop k+1 needs only column c of hop k) and a
+// tile is closed under the graph's edges (tiles are whole graphs of the block-diagonal batch — the caller
+// guarantees it).  What it buys: hop k+1 gathers rows this very CTA stored a few microseconds earlier, so the
+// first touch of every row slice is an L2 hit instead of a DRAM miss, the edge records and row pointers of the
+// tile are re-read from cache, and two of every three launches (with their ramp-up / drain) disappear.
+// Rows written inside the launch are read with plain (coherent) loads, never through the non-coherent path.
+// Same summation order and rounding as every other K1 variant (bit-identical).
+struct HopArgs {
+  const float* in[DC_MAX_CHAIN];
+  const float* add[DC_MAX_CHAIN];
+  float* out[DC_MAX_CHAIN];
+  unsigned ldin[DC_MAX_CHAIN], ldadd[DC_MAX_CHAIN], ldout[DC_MAX_CHAIN];
+};
+
+__device__ __forceinline__ float4 ld_coherent4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+spmm_chain_kernel(const int32_t* __restrict__ rowptr, const int2* __restrict__ edges, const float* __restrict__ self_w,
+                  const HopArgs hops, int num_hops, int N, int self_loop, const int32_t* __restrict__ tile_ptr, int n_slices,
+                  int tile_nodes) {
+  const int slice = blockIdx.x % n_slices;
+  const int tile = blockIdx.x / n_slices;
+  const int t0 = tile_ptr ? tile_ptr[tile] : tile * tile_nodes;
+  const int t1 = tile_ptr ? tile_ptr[tile + 1] : min(N, t0 + tile_nodes);
+  const int col = slice * 32 + (threadIdx.x & 7) * 4;
+
+  for (int hop = 0; hop < num_hops; ++hop) {
+    const float* hcol = hops.in[hop] + col;
+    const size_t ldh_b = (size_t)hops.ldin[hop];
+    const float* add = hops.add[hop];
+    const unsigned ldadd = hops.ldadd[hop], ldo = hops.ldout[hop];
+    float* out = hops.out[hop];
+    int node = t0 + (threadIdx.x >> 3);
+    int beg = 0, end = 0, begn = 0, endn = 0;
+    if (node < t1) { beg = __ldg(rowptr + node); end = __ldg(rowptr + node + 1); }
+    if (node + 128 < t1) { begn = __ldg(rowptr + node + 128); endn = __ldg(rowptr + node + 129); }
+    for (; node < t1; node += 128) {
+      int beg2 = 0, end2 = 0;
+      if (node + 256 < t1) { beg2 = __ldg(rowptr + node + 256); end2 = __ldg(rowptr + node + 257); }
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (add != nullptr) acc = ld_coherent4(add + (size_t)((unsigned)node * ldadd) + col);
+      int p = beg;
+      for (; p + 8 <= end; p += 8) {
+        int2 e[8];
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) e[u] = ldg_edge(edges + p + u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = ld_coherent4(hcol + (size_t)(unsigned)e[u].x * ldh_b);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc_mul_add(acc, __int_as_float(e[u].y), v[u]);
+      }
+      if (p + 4 <= end) {
+        int2 e[4];
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) e[u] = ldg_edge(edges + p + u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld_coherent4(hcol + (size_t)(unsigned)e[u].x * ldh_b);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc_mul_add(acc, __int_as_float(e[u].y), v[u]);
+        p += 4;
+      }
+      for (; p < end; ++p) {
+        const int2 e = ldg_edge(edges + p);
+        acc_mul_add(acc, __int_as_float(e.y), ld_coherent4(hcol + (size_t)(unsigned)e.x * ldh_b));
+      }
+      if (self_loop) acc_mul_add(acc, self_w[node], ld_coherent4(hcol + (size_t)(unsigned)node * ldh_b));
+      *reinterpret_cast<float4*>(out + (size_t)((unsigned)node * ldo) + col) = acc;
+      beg = begn; end = endn; begn = beg2; endn = end2;
+    }
+    __syncthreads();   // every row slice of this hop is stored (and visible to the block) before the next hop gathers it
+  }
+}
+
 // packed (neighbour, weight bits) records in CSR order; w == NULL -> weight 1
 __global__ void pack_edges_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ w, int64_t E, int2* __restrict__ out) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -663,6 +746,51 @@ extern "C" int dc_spmm_lean(const int32_t* rowptr, const void* edges, const floa
     spmm_lean_kernel<false><<<grid, 1024, 0, st>>>(rowptr, static_cast<const int2*>(edges), self_w, h, (unsigned)ldh, out,
                                                    (unsigned)ldo, add, (unsigned)ldadd, (int)N, F, self_loop, bias, relu, tile_ptr,
                                                    n_slices, tile_nodes);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+extern "C" int dc_spmm_chain(const int32_t* rowptr, const void* edges, const float* self_w, const dc_hop_t* hops, int32_t num_hops,
+                             int64_t N, int32_t F, int self_loop, const int32_t* tile_ptr, int64_t n_tiles, int32_t tile_nodes,
+                             dc_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DC_REQUIRE(N >= 0 && F >= 0 && num_hops >= 0, DC_EINVAL, "spmm_chain: negative size");
+  if (N == 0 || F == 0 || num_hops == 0) return DC_OK;
+  DC_REQUIRE(num_hops <= DC_MAX_CHAIN, DC_EINVAL, "spmm_chain: at most %d hops", DC_MAX_CHAIN);
+  DC_REQUIRE(rowptr && hops, DC_EINVAL, "spmm_chain: null pointer");
+  DC_REQUIRE(!self_loop || self_w, DC_EINVAL, "spmm_chain: self_loop needs self_w");
+  DC_REQUIRE(F % 32 == 0 && (!edges || (reinterpret_cast<uintptr_t>(edges) & 7) == 0), DC_ENOSUP,
+             "spmm_chain: needs F %% 32 == 0 (use one dc_spmm_lean per hop)");
+  DC_REQUIRE(N < (1ll << 31), DC_ENOSUP, "spmm_chain: N exceeds 32-bit offsets");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  HopArgs a;
+  for (int k = 0; k < DC_MAX_CHAIN; ++k) {
+    const dc_hop_t& hp = hops[k < num_hops ? k : 0];
+    if (k < num_hops) {
+      DC_REQUIRE(hp.in && hp.out && hp.in != hp.out, DC_EINVAL, "spmm_chain: hop %d: null / aliased in and out", k);
+      DC_REQUIRE(hp.ldin % 4 == 0 && hp.ldout % 4 == 0 && hp.ldin >= F && hp.ldout >= F && al16(hp.in) && al16(hp.out) &&
+                     (!hp.add || (hp.ldadd % 4 == 0 && hp.ldadd >= F && al16(hp.add))),
+                 DC_ENOSUP, "spmm_chain: hop %d: needs 16-byte aligned rows", k);
+      DC_REQUIRE((uint64_t)N * (uint64_t)hp.ldout < (1ull << 32) && (uint64_t)N * (uint64_t)hp.ldin < (1ull << 32) &&
+                     (!hp.add || (uint64_t)N * (uint64_t)hp.ldadd < (1ull << 32)),
+                 DC_ENOSUP, "spmm_chain: hop %d: N*ld exceeds 32-bit element offsets", k);
+    }
+    a.in[k] = hp.in; a.add[k] = hp.add; a.out[k] = hp.out;
+    a.ldin[k] = (unsigned)hp.ldin; a.ldadd[k] = (unsigned)hp.ldadd; a.ldout[k] = (unsigned)hp.ldout;
+  }
+  if (!tile_ptr) {
+    DC_REQUIRE(tile_nodes > 0, DC_EINVAL, "spmm_chain: tile_nodes must be > 0 without tile_ptr");
+    n_tiles = cdiv(N, tile_nodes);
+  }
+  DC_REQUIRE(n_tiles > 0, DC_EINVAL, "spmm_chain: no tiles");
+  const int n_slices = F / 32;
+  static bool carve = false;
+  if (!carve) {
+    cudaFuncSetAttribute(spmm_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    carve = true;
+  }
+  spmm_chain_kernel<<<(unsigned)(n_tiles * n_slices), 1024, 0, st>>>(rowptr, static_cast<const int2*>(edges), self_w, a, num_hops,
+                                                                     (int)N, self_loop, tile_ptr, n_slices, tile_nodes);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

@@ -78,9 +78,8 @@ class _TAGConvFn(torch.autograd.Function):
         if K > 0:
             buf = torch.empty((N, K * Fi), dtype=x.dtype, device=x.device)
             for k in range(K):
-                hk = buf[:, k * Fi:(k + 1) * Fi]
-                g.propagate(hs[-1], out=hk)
-                hs.append(hk)
+                hs.append(buf[:, k * Fi:(k + 1) * Fi])
+            ops.propagate_chain(g, [(hs[k], None, hs[k + 1]) for k in range(K)])   # h_{k+1} = A_hat h_k
         out = ops.gemm([(h, w) for h, w in zip(hs, weights)], N, Fo, False, True, bias=bias, relu=relu,
                        precision=precision)
         ctx.g, ctx.relu, ctx.precision, ctx.has_bias = g, relu, precision, bias is not None
@@ -108,9 +107,15 @@ class _TAGConvFn(torch.autograd.Function):
         dx = None
         if need_x:
             gk = ops.gemm([(dout, weights[K])], N, Fi, False, False, precision=ctx.precision)
-            for k in range(K - 1, -1, -1):
-                dhk = ops.gemm([(dout, weights[k])], N, Fi, False, False, precision=ctx.precision)
-                gk = g.propagate(gk, transpose=True, add=dhk)
+            if ops.K1_CHAIN >= 2 and K > 0:
+                # all dH_k first, then the transposed hops as one chain, accumulating in place: dH_{k-1} += A_hat^T g_k
+                dhs = [ops.gemm([(dout, weights[k])], N, Fi, False, False, precision=ctx.precision) for k in range(K)] + [gk]
+                ops.propagate_chain(g, [(dhs[k + 1], dhs[k], dhs[k]) for k in range(K - 1, -1, -1)], transpose=True)
+                gk = dhs[0]
+            else:
+                for k in range(K - 1, -1, -1):
+                    dhk = ops.gemm([(dout, weights[k])], N, Fi, False, False, precision=ctx.precision)
+                    gk = g.propagate(gk, transpose=True, add=dhk)
             dx = gk
         return (dx, None, db, None, None, *dws)
 

@@ -102,6 +102,8 @@ K1_VARIANT = os.environ.get("DCB200_K1", "auto")
 # dc_spmm_blocks flags: 1 = persistent grid, 2 = L1 record prefetch, 4 = 768-thread CTAs, 8/16 = L2 prefetch stream
 # (24 = the CTA's own tile slice), 32 = one prefetch per sector.  28 = 768 threads, one-shot grid, in-CTA L2 stream.
 K1_FLAGS = int(os.environ.get("DCB200_K1_FLAGS", "28"))
+# hop chain (K1 v9): 0 = one launch per hop; 1 = chain the forward hops of a layer; 2 = forward and backward chains
+K1_CHAIN = int(os.environ.get("DCB200_K1_CHAIN", "1"))
 
 
 def make_tiles(ptr_host, num_nodes, target=TILE_NODES):
@@ -159,6 +161,8 @@ class GraphCSR:
         self.tile_ptr = (torch.tensor(tiles, dtype=_i32, device=edge_index.device) if tiles is not None else None)
         self.n_tiles = len(tiles) - 1 if tiles is not None else 0
         self._tiles_host = tiles
+        # every tile boundary is a graph boundary <=> tiles are closed under the edges (needed by the hop chain)
+        self.tiles_closed = tiles is not None and set(tiles) <= set(ptr_host)
         self._blocks = {}
         self._max_tile = max((b - a for a, b in zip(tiles[:-1], tiles[1:])), default=0) if tiles is not None else TILE_NODES
 
@@ -202,6 +206,20 @@ class GraphCSR:
 
 def _al16(t):
     return t is None or (t.data_ptr() % 16 == 0)
+
+
+def propagate_chain(g, hops, transpose=False):
+    """Consecutive hops of one layer: ``hops`` = [(in, add or None, out)], ``in`` of hop k normally the ``out`` of hop
+    k-1.  One dc_spmm_chain launch when the structure allows it (block-diagonal batch with whole-graph tiles, F % 32 == 0,
+    TAG/GCN weights), else one ``propagate`` per hop; both give bit-identical results."""
+    F = hops[0][0].shape[1]
+    ok = (K1_CHAIN and g.mode in ("tag", "gcn") and g.tiles_closed and F % 32 == 0 and len(hops) <= _abi.MAX_CHAIN
+          and K1_VARIANT in ("auto", "lean", "blocks") and all(_tiled_ok(h, o, a, None) for h, a, o in hops))
+    if not ok:
+        return [g.propagate(h, transpose=transpose, add=a, out=o) for h, a, o in hops]
+    rp = g.t[0] if transpose else g.rowptr
+    return spmm_chain(rp, g._edges_t if transpose else g.edges, g.self_w if g.mode == "gcn" else None, hops,
+                      self_loop=g.mode == "gcn", tile_ptr=g.tile_ptr, n_tiles=g.n_tiles)
 
 
 def _tiled_ok(h, out, add, bias):
@@ -349,6 +367,27 @@ def spmm_lean(rowptr, edges, self_w, h, add=None, self_loop=False, bias=None, re
         _prof_end(e0, op="spmm", F=F, N=N, E=E,
                   bytes=8 * N * F + 4 * E + 8 * N + 4 + (4 * N * F if add is not None else 0))
     return out
+
+
+def spmm_chain(rowptr, edges, self_w, hops, self_loop=False, tile_ptr=None, n_tiles=0, tile_nodes=TILE_NODES):
+    """K1 v9: ``hops`` = [(in, add or None, out), ...] consecutive hops of one layer in ONE launch (see dc_spmm_chain);
+    every tile must be closed under the edges (``GraphCSR.tiles_closed``)."""
+    arr = (_abi.Hop * len(hops))()
+    N, F = hops[0][0].shape
+    nbytes = 0
+    for i, (h, add, out) in enumerate(hops):
+        _need(h, _f32, "in"); _need(add, _f32, "add"); _need(out, _f32, "out")
+        if h.shape != (N, F) or out.shape != (N, F) or (add is not None and add.shape != (N, F)):
+            raise _abi.DcError("spmm_chain: every hop needs [N, F] operands")
+        arr[i] = _abi.Hop(_ptr(h), _rows(h, "in"), _ptr(add), _rows(add, "add") if add is not None else 0, _ptr(out),
+                          _rows(out, "out"))
+        nbytes += 8 * N * F + 4 * edges.shape[0] + 8 * N + 4 + (4 * N * F if add is not None else 0)
+    e0 = _prof_begin()
+    _abi.call("dc_spmm_chain", _ptr(rowptr), _ptr(edges), _ptr(self_w), arr, len(hops), N, F, int(bool(self_loop)), _ptr(tile_ptr),
+              int(n_tiles), int(tile_nodes), _stream())
+    if e0 is not None:
+        _prof_end(e0, op="spmm", F=F, N=N, E=edges.shape[0], bytes=nbytes, hops=len(hops))
+    return [h[2] for h in hops]
 
 
 def spmm_tiled(rowptr, nbr, w, self_w, h, add=None, self_loop=False, bias=None, relu=False, out=None, tile_ptr=None,

@@ -90,9 +90,9 @@ def tag_conv(x: Tensor, edge_index: Tensor, weights: List[Tensor], bias: Optiona
     buf = torch.empty((N, max(K, 1) * Fi), dtype=x.dtype, device=x.device)
     hs = [x]
     for k in range(K):
-        hk = buf[:, k * Fi:(k + 1) * Fi]
-        g.propagate(hs[-1], out=hk)
-        hs.append(hk)
+        hs.append(buf[:, k * Fi:(k + 1) * Fi])
+    if K:
+        ops.propagate_chain(g, [(hs[k], None, hs[k + 1]) for k in range(K)])   # h_{k+1} = A_hat h_k (one launch, K1 v9)
     out = ops.gemm([(h, w) for h, w in zip(hs, weights)], N, weights[0].shape[0], False, True, bias=bias, relu=relu,
                    precision=precision)
     return out, buf
@@ -126,9 +126,15 @@ def tag_conv_backward(dout: Tensor, out: Tensor, x: Tensor, hops: Tensor, edge_i
     db = ops.colsum(dout) if need_db else dout.new_empty(0)
     if need_dx:
         gk = ops.gemm([(dout, weights[K])], N, Fi, False, False, precision=precision)
-        for k in range(K - 1, -1, -1):
-            dhk = ops.gemm([(dout, weights[k])], N, Fi, False, False, precision=precision)
-            gk = g.propagate(gk, transpose=True, add=dhk)
+        if ops.K1_CHAIN >= 2 and K > 0:
+            # all dH_k first, then the transposed hops as one chain, accumulating in place: dH_{k-1} += A_hat^T g_k
+            dhs = [ops.gemm([(dout, weights[k])], N, Fi, False, False, precision=precision) for k in range(K)] + [gk]
+            ops.propagate_chain(g, [(dhs[k + 1], dhs[k], dhs[k]) for k in range(K - 1, -1, -1)], transpose=True)
+            gk = dhs[0]
+        else:
+            for k in range(K - 1, -1, -1):
+                dhk = ops.gemm([(dout, weights[k])], N, Fi, False, False, precision=precision)
+                gk = g.propagate(gk, transpose=True, add=dhk)
         dx = gk
     else:
         dx = dout.new_empty(0)

@@ -104,6 +104,21 @@ DC_API int dc_spmm_tiled(const int32_t* rowptr, const int32_t* nbr, const float*
                          int32_t F, int self_loop, const float* bias, int relu, const int32_t* tile_ptr,
                          int64_t n_tiles, int32_t tile_nodes, int variant, dc_stream_t stream);
 
+/* K1 v9 (hop chain): up to DC_MAX_CHAIN consecutive hops in one launch; hop k computes
+ *   out_k = add_k + A in_k      (same rows, records, order and rounding as dc_spmm_lean; bit-identical)
+ * where in_k may be out_{k-1} (TAGConv forward h_{k+1} = A h_k, models/model.py:71,77 via PyG tag_conv.py; backward
+ * g_{k-1} = dH_{k-1} + A^T g_k on the transposed records).  add_k may equal out_k (in place).  A CTA keeps its
+ * (tile, 128-byte slice) across the hops, so REQUIRES every tile to be closed under the edges (whole graphs of a
+ * block-diagonal batch: tile_ptr built from Batch.ptr without splitting a graph) and F % 32 == 0. */
+#define DC_MAX_CHAIN 4
+typedef struct dc_hop {
+  const float* in; int64_t ldin;
+  const float* add; int64_t ldadd;   /* NULL: no addend */
+  float* out; int64_t ldout;
+} dc_hop_t;
+DC_API int dc_spmm_chain(const int32_t* rowptr, const void* edges, const float* self_w, const dc_hop_t* hops, int32_t num_hops,
+                  int64_t num_nodes, int32_t F, int self_loop, const int32_t* tile_ptr, int64_t n_tiles, int32_t tile_nodes,
+                  dc_stream_t stream);
 /* K1 v6 ("lean"): the same tile x 128-byte-slice mapping driven by packed 8-byte edge records
  * {int32 neighbour, fp32 weight} in CSR order (dc_pack_edges; w == NULL -> weight 1): one uniform 64-bit
  * load per edge instead of index/weight loads + shuffles, 8 row gathers in flight per lane, no predicates on

@@ -368,3 +368,64 @@ def test_gemm_tcgen05_weight_gradient(dc, K, M, N):
     acc = out.clone()
     dc.ops.gemm([(A, B)], M, N, True, False, out=acc, accumulate=True, precision=dc.ops.GEMM_TF32X3)
     assert_close(acc, (2 * ref).float(), what="tcgen05 dW gemm accumulate")
+
+
+@pytest.mark.parametrize("F", [32, 256])
+def test_hop_chain_bit_identical_to_single_hops(dc, F):
+    """K1 v9: the hops of a layer in one launch == one launch per hop == generic kernel, bit for bit (forward and
+    transposed with in-place addends), ragged block-diagonal batch with isolated nodes, deep rows and an empty graph."""
+    from deformcontact_b200 import ops
+    sizes = [700, 0, 1, 1300, 64]
+    ptr = [0]
+    for s_ in sizes:
+        ptr.append(ptr[-1] + s_)
+    N = ptr[-1]
+    gen = torch.Generator().manual_seed(5)
+    eis = []
+    for lo, hi in zip(ptr[:-1], ptr[1:]):
+        n = hi - lo
+        if n == 0:
+            continue
+        e = torch.randint(0, n, (2, 9 * n), generator=gen)
+        e[1, : min(n, 200)] = 0          # one deep row (> 64 edges)
+        eis.append(e + lo)
+    ei = torch.cat(eis, 1).cuda()
+    g = ops.GraphCSR(ei, N, "tag", ptr)
+    assert g.tiles_closed
+    x = torch.randn(N, F, generator=gen).cuda()
+    # forward chain into the strided [N, 3F] layout TAGConv uses
+    buf = torch.zeros(N, 3 * F, device="cuda")
+    hs = [x] + [buf[:, i * F:(i + 1) * F] for i in range(3)]
+    ops.spmm_chain(g.rowptr, g.edges, None, [(hs[i], None, hs[i + 1]) for i in range(3)], tile_ptr=g.tile_ptr, n_tiles=g.n_tiles)
+    ref = x
+    for i in range(3):
+        ref = ops.spmm(g.rowptr, g.nbr, ref, dis=g.dis)
+        assert torch.equal(hs[i + 1], ref), f"forward hop {i}"
+    # transposed chain with in-place addends
+    adds = [torch.randn(N, F, generator=gen).cuda() for _ in range(3)]
+    d = [a.clone() for a in adds]
+    g3 = torch.randn(N, F, generator=gen).cuda()
+    ops.spmm_chain(g.t[0], g._edges_t, None, [(g3, d[2], d[2]), (d[2], d[1], d[1]), (d[1], d[0], d[0])], tile_ptr=g.tile_ptr,
+                   n_tiles=g.n_tiles)
+    ref = g3
+    for i in (2, 1, 0):
+        ref = ops.spmm(g.t[0], g.t[1], ref, dis=g.dis, add=adds[i])
+        assert torch.equal(d[i], ref), f"transposed hop {i}"
+    # propagate_chain falls back to single hops when a graph is split across tiles (tiles not closed)
+    big = ops.GraphCSR(ei, N, "tag", [0, N])
+    if not big.tiles_closed:
+        out = [torch.empty(N, F, device="cuda") for _ in range(2)]
+        ops.propagate_chain(big, [(x, None, out[0]), (out[0], None, out[1])])
+        assert torch.equal(out[0], hs[1])
+
+
+def test_hop_chain_rejects_bad_args(dc):
+    from deformcontact_b200 import ops, _abi
+    ei = torch.randint(0, 100, (2, 500)).cuda()
+    g = ops.GraphCSR(ei, 100, "tag", [0, 100])
+    x = torch.randn(100, 24).cuda()
+    with pytest.raises(_abi.DcError):      # F % 32 != 0
+        ops.spmm_chain(g.rowptr, g.edges, None, [(x, None, torch.empty_like(x))], tile_ptr=g.tile_ptr, n_tiles=g.n_tiles)
+    x = torch.randn(100, 32).cuda()
+    with pytest.raises(_abi.DcError):      # in aliases out
+        ops.spmm_chain(g.rowptr, g.edges, None, [(x, None, x)], tile_ptr=g.tile_ptr, n_tiles=g.n_tiles)
