@@ -1,11 +1,13 @@
 // K4 — kNN / radius neighbour search (torch_cluster.knn_graph / radius_graph semantics as called
 // at utils/pointcloud_utils.py:10,12).  Tiled brute force: a CTA stages TILE candidate points in
-// shared memory; each warp owns QPW queries and evaluates 32 candidates per step (one per lane)
-// against all of them; survivors of the "better than the current k-th" test are inserted with
-// warp shuffles into a per-query candidate set spread across the lanes; a warp-shuffle bitonic
-// sort orders the final set.  Keys are (fp32 distance bits << 32 | index): one unsigned compare
-// gives "ascending distance, lower index wins ties".  Distances use individually rounded
-// mul/add in a fixed association so they are bit-identical to the oracle's.
+// shared memory; each warp owns QW queries (8 for k <= 31) and evaluates 64 candidates per step (two per
+// lane) against all of them with no synchronisation — 2*QW independent distance chains per lane — then
+// one warp vote tells whether any pair beat its query's current k-th distance (a 32-bit compare on the
+// distance bits); only then the survivors are inserted with warp shuffles into a per-query candidate
+// set spread across the lanes.  A warp-shuffle bitonic sort orders the final set.  Keys are
+// (fp32 distance bits << 32 | index): one unsigned compare gives "ascending distance, lower index
+// wins ties".  Distances use individually rounded mul/add in a fixed association so they are
+// bit-identical to the oracle's.
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -76,34 +78,85 @@ __device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&k)[SLOTS]
   }
 }
 
+// One candidate (already tested against the 32-bit prefilter by the caller's ballot) set: insert every lane's
+// surviving key into query qi's lane-distributed top-k set, in ballot order.
 template <int SLOTS>
+__device__ __forceinline__ void knn_insert(unsigned long long (&keys)[SLOTS], unsigned long long& thresh, unsigned& thr_hi,
+                                           unsigned long long key, int lane) {
+  unsigned m = __ballot_sync(0xffffffffu, key < thresh);
+  while (m) {
+    const int b = __ffs(m) - 1;
+    m &= m - 1;
+    const unsigned long long ck = shfl64(key, b);
+    if (ck < thresh) {
+      // locate the current maximum of the set, replace it, recompute the threshold
+      unsigned long long lmax = keys[0];
+      int lslot = 0;
+#pragma unroll
+      for (int s = 1; s < SLOTS; ++s)
+        if (keys[s] > lmax) { lmax = keys[s]; lslot = s; }
+      unsigned long long wmax = lmax;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = shfl_xor64(wmax, o);
+        wmax = t > wmax ? t : wmax;
+      }
+      const int owner = __ffs(__ballot_sync(0xffffffffu, lmax == wmax)) - 1;
+      if (lane == owner) {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s)
+          if (s == lslot) keys[s] = ck;
+      }
+      lmax = keys[0];
+#pragma unroll
+      for (int s = 1; s < SLOTS; ++s) lmax = keys[s] > lmax ? keys[s] : lmax;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = shfl_xor64(lmax, o);
+        lmax = t > lmax ? t : lmax;
+      }
+      thresh = lmax;
+      thr_hi = (unsigned)(lmax >> 32);
+    }
+  }
+}
+
+// QW queries per warp; every step evaluates 64 candidates (two per lane) against all QW queries with no
+// synchronisation at all (2*QW independent distance chains per lane), then ONE warp vote decides whether any pair
+// beat its query's current k-th distance; only then the (rare, after the first few hundred candidates) insertion
+// path runs.  Invalid queries carry NaN coordinates and a zero threshold, so they never vote.
+template <int SLOTS, int QW>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, int64_t B, int64_t N, int kk, int loop, int W,
            int32_t* __restrict__ out) {
   __shared__ float sx[TILE], sy[TILE], sz[TILE];
+  constexpr int QB = KNN_WARPS * QW;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t qb0 = (int64_t)blockIdx.x * QPB;
-  const int64_t qb1 = min(N, qb0 + QPB) - 1;
+  const int64_t qb0 = (int64_t)blockIdx.x * QB;
+  const int64_t qb1 = min(N, qb0 + QB) - 1;
   const int64_t cand_lo = ptr[find_graph(ptr, B, qb0)];
   const int64_t cand_hi = ptr[find_graph(ptr, B, qb1) + 1];
 
-  float qx[QPW], qy[QPW], qz[QPW];
-  int64_t lo[QPW], hi[QPW];
-  bool qv[QPW];
-  unsigned long long keys[QPW][SLOTS], thresh[QPW];
+  float qx[QW], qy[QW], qz[QW];
+  int64_t lo[QW], hi[QW];
+  bool qv[QW];
+  unsigned long long keys[QW][SLOTS], thresh[QW];
+  unsigned thr_hi[QW];
   constexpr int CAP = 32 * SLOTS;
 #pragma unroll
-  for (int qi = 0; qi < QPW; ++qi) {
-    const int64_t q = qb0 + warp * QPW + qi;
+  for (int qi = 0; qi < QW; ++qi) {
+    const int64_t q = qb0 + warp * QW + qi;
     qv[qi] = q < N;
     const int64_t qq = qv[qi] ? q : (N - 1);
     const int g = find_graph(ptr, B, qq);
     lo[qi] = ptr[g];
     hi[qi] = ptr[g + 1];
-    qx[qi] = pos[3 * qq]; qy[qi] = pos[3 * qq + 1]; qz[qi] = pos[3 * qq + 2];
+    const float nan = __int_as_float(0x7fc00000);
+    qx[qi] = qv[qi] ? pos[3 * qq] : nan; qy[qi] = qv[qi] ? pos[3 * qq + 1] : nan; qz[qi] = qv[qi] ? pos[3 * qq + 2] : nan;
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) keys[qi][s] = (s * 32 + lane) < kk ? KEY_INF : 0ull;  // 0 = permanently unused slot
-    thresh[qi] = KEY_INF;
+    thresh[qi] = qv[qi] ? KEY_INF : 0ull;
+    thr_hi[qi] = qv[qi] ? 0xffffffffu : 0u;
   }
 
   for (int64_t t0 = cand_lo; t0 < cand_hi; t0 += TILE) {
@@ -114,60 +167,46 @@ knn_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, int64
       sx[i] = pos[3 * c]; sy[i] = pos[3 * c + 1]; sz[i] = pos[3 * c + 2];
     }
     __syncthreads();
-    // whole tile inside a query's own point cloud (the common case: one graph per CTA) -> no per-candidate range test
-    bool inside[QPW];
+    // whole tile inside every valid query's own point cloud (the common case: one graph per CTA) -> no range tests
+    bool all_inside = true;
 #pragma unroll
-    for (int qi = 0; qi < QPW; ++qi) inside[qi] = qv[qi] && t0 >= lo[qi] && t0 + tile_n <= hi[qi];
-    for (int j0 = 0; j0 < tile_n; j0 += 32) {
-      const int j = j0 + lane;
-      const bool inb = j < tile_n;
-      const float px = inb ? sx[j] : 0.f, py = inb ? sy[j] : 0.f, pz = inb ? sz[j] : 0.f;
-      const int64_t c = t0 + j;
+    for (int qi = 0; qi < QW; ++qi) all_inside = all_inside && (!qv[qi] || (t0 >= lo[qi] && t0 + tile_n <= hi[qi]));
+    for (int j0 = 0; j0 < tile_n; j0 += 64) {
+      // TILE is a multiple of 64, so both reads stay inside the arrays (stale values past tile_n are masked below)
+      const int ja = j0 + lane, jb = ja + 32;
+      const float pxa = sx[ja], pya = sy[ja], pza = sz[ja];
+      const float pxb = sx[jb], pyb = sy[jb], pzb = sz[jb];
+      const int64_t ca = t0 + ja, cb = t0 + jb;
+      unsigned da[QW], db[QW];
+      bool pass = false;
+      if (all_inside && j0 + 64 <= tile_n) {
 #pragma unroll
-      for (int qi = 0; qi < QPW; ++qi) {
-        const float d = sqdist(qx[qi], qy[qi], qz[qi], px, py, pz);
-        // cheap pre-filter on the distance bits (d >= 0: unsigned order == float order); ties on the distance fall
-        // through to the exact (distance, index) compare below
-        const unsigned dbits = __float_as_uint(d);
-        const bool ok = inb && (inside[qi] || (qv[qi] && c >= lo[qi] && c < hi[qi]));
-        unsigned m = __ballot_sync(0xffffffffu, ok && dbits <= (unsigned)(thresh[qi] >> 32));
-        if (m == 0) continue;
-        const unsigned long long key = ok ? (((unsigned long long)dbits << 32) | (unsigned)c) : KEY_INF;
-        m = __ballot_sync(0xffffffffu, key < thresh[qi]);
-        while (m) {
-          const int b = __ffs(m) - 1;
-          m &= m - 1;
-          const unsigned long long ck = shfl64(key, b);
-          if (ck < thresh[qi]) {
-            // locate the current maximum of the set, replace it, recompute the threshold
-            unsigned long long lmax = keys[qi][0];
-            int lslot = 0;
+        for (int qi = 0; qi < QW; ++qi) {
+          da[qi] = __float_as_uint(sqdist(qx[qi], qy[qi], qz[qi], pxa, pya, pza));
+          db[qi] = __float_as_uint(sqdist(qx[qi], qy[qi], qz[qi], pxb, pyb, pzb));
+          // d >= 0 (or NaN for an invalid query): unsigned order == float order; ties on the distance go on to the exact compare
+          pass = pass || da[qi] <= thr_hi[qi] || db[qi] <= thr_hi[qi];
+        }
+        if (!__any_sync(0xffffffffu, pass)) continue;
 #pragma unroll
-            for (int s = 1; s < SLOTS; ++s)
-              if (keys[qi][s] > lmax) { lmax = keys[qi][s]; lslot = s; }
-            unsigned long long wmax = lmax;
+        for (int qi = 0; qi < QW; ++qi) {
+          if (__ballot_sync(0xffffffffu, da[qi] <= thr_hi[qi]))
+            knn_insert<SLOTS>(keys[qi], thresh[qi], thr_hi[qi], ((unsigned long long)da[qi] << 32) | (unsigned)ca, lane);
+          if (__ballot_sync(0xffffffffu, db[qi] <= thr_hi[qi]))
+            knn_insert<SLOTS>(keys[qi], thresh[qi], thr_hi[qi], ((unsigned long long)db[qi] << 32) | (unsigned)cb, lane);
+        }
+      } else {
+        const bool inba = ja < tile_n, inbb = jb < tile_n;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              unsigned long long t = shfl_xor64(wmax, o);
-              wmax = t > wmax ? t : wmax;
-            }
-            const int owner = __ffs(__ballot_sync(0xffffffffu, lmax == wmax)) - 1;
-            if (lane == owner) {
-#pragma unroll
-              for (int s = 0; s < SLOTS; ++s)
-                if (s == lslot) keys[qi][s] = ck;
-            }
-            // new maximum
-            lmax = keys[qi][0];
-#pragma unroll
-            for (int s = 1; s < SLOTS; ++s) lmax = keys[qi][s] > lmax ? keys[qi][s] : lmax;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              unsigned long long t = shfl_xor64(lmax, o);
-              lmax = t > lmax ? t : lmax;
-            }
-            thresh[qi] = lmax;
-          }
+        for (int qi = 0; qi < QW; ++qi) {
+          const bool oka = inba && qv[qi] && ca >= lo[qi] && ca < hi[qi];
+          const bool okb = inbb && qv[qi] && cb >= lo[qi] && cb < hi[qi];
+          const unsigned a = __float_as_uint(sqdist(qx[qi], qy[qi], qz[qi], pxa, pya, pza));
+          const unsigned b = __float_as_uint(sqdist(qx[qi], qy[qi], qz[qi], pxb, pyb, pzb));
+          if (__ballot_sync(0xffffffffu, oka && a <= thr_hi[qi]))
+            knn_insert<SLOTS>(keys[qi], thresh[qi], thr_hi[qi], oka ? (((unsigned long long)a << 32) | (unsigned)ca) : KEY_INF, lane);
+          if (__ballot_sync(0xffffffffu, okb && b <= thr_hi[qi]))
+            knn_insert<SLOTS>(keys[qi], thresh[qi], thr_hi[qi], okb ? (((unsigned long long)b << 32) | (unsigned)cb) : KEY_INF, lane);
         }
       }
     }
@@ -175,8 +214,8 @@ knn_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, int64
 
   const int ndummy = CAP - kk;
 #pragma unroll
-  for (int qi = 0; qi < QPW; ++qi) {
-    const int64_t q = qb0 + warp * QPW + qi;
+  for (int qi = 0; qi < QW; ++qi) {
+    const int64_t q = qb0 + warp * QW + qi;
     if (!qv[qi]) continue;  // warp-uniform
     warp_bitonic_sort<SLOTS>(keys[qi], lane);
     // rank of the self match among the real entries (or CAP if absent / loop)
@@ -322,10 +361,10 @@ extern "C" int dc_knn(const float* pos, const int64_t* ptr, int64_t B, int64_t N
   DC_REQUIRE(pos && ptr && nbr_out, DC_EINVAL, "knn: null pointer");
   const int kk = k + (loop ? 0 : 1);
   DC_REQUIRE(kk <= 128, DC_ENOSUP, "knn: k=%d exceeds the supported maximum (127, or 128 with loop)", k);
-  const unsigned grid = (unsigned)cdiv(N, QPB);
-  if (kk <= 32) knn_kernel<1><<<grid, KNN_THREADS, 0, st>>>(pos, ptr, B, N, kk, loop, kk, nbr_out);
-  else if (kk <= 64) knn_kernel<2><<<grid, KNN_THREADS, 0, st>>>(pos, ptr, B, N, kk, loop, kk, nbr_out);
-  else knn_kernel<4><<<grid, KNN_THREADS, 0, st>>>(pos, ptr, B, N, kk, loop, kk, nbr_out);
+  // 8 queries per warp while the candidate set is one key per lane; fewer for wide sets (register budget)
+  if (kk <= 32) knn_kernel<1, 8><<<(unsigned)cdiv(N, KNN_WARPS * 8), KNN_THREADS, 0, st>>>(pos, ptr, B, N, kk, loop, kk, nbr_out);
+  else if (kk <= 64) knn_kernel<2, 4><<<(unsigned)cdiv(N, KNN_WARPS * 4), KNN_THREADS, 0, st>>>(pos, ptr, B, N, kk, loop, kk, nbr_out);
+  else knn_kernel<4, 4><<<(unsigned)cdiv(N, KNN_WARPS * 4), KNN_THREADS, 0, st>>>(pos, ptr, B, N, kk, loop, kk, nbr_out);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

@@ -103,7 +103,7 @@ K1_VARIANT = os.environ.get("DCB200_K1", "auto")
 # (24 = the CTA's own tile slice), 32 = one prefetch per sector.  28 = 768 threads, one-shot grid, in-CTA L2 stream.
 K1_FLAGS = int(os.environ.get("DCB200_K1_FLAGS", "28"))
 # hop chain (K1 v9): 0 = one launch per hop; 1 = chain the forward hops of a layer; 2 = forward and backward chains
-K1_CHAIN = int(os.environ.get("DCB200_K1_CHAIN", "1"))
+K1_CHAIN = int(os.environ.get("DCB200_K1_CHAIN", "2"))
 
 
 def make_tiles(ptr_host, num_nodes, target=TILE_NODES):
