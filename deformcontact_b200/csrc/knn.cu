@@ -80,6 +80,16 @@ __device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&k)[SLOTS]
 
 // One candidate (already tested against the 32-bit prefilter by the caller's ballot) set: insert every lane's
 // surviving key into query qi's lane-distributed top-k set, in ballot order.
+// Warp-wide maximum of 64-bit keys with two 32-bit REDUX operations (high words, then low words among the lanes
+// that hold the maximal high word).
+__device__ __forceinline__ unsigned long long warp_max64(unsigned long long v) {
+  const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(v >> 32));
+  const unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(v >> 32) == hi ? (unsigned)v : 0u);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+// Insert every lane's surviving key into a query's lane-distributed top-k set, in lane order.  Invariant:
+// `thresh` is the maximum of the set (KEY_INF placeholders included), so the slot to replace is the one equal to it.
 template <int SLOTS>
 __device__ __forceinline__ void knn_insert(unsigned long long (&keys)[SLOTS], unsigned long long& thresh, unsigned& thr_hi,
                                            unsigned long long key, int lane) {
@@ -89,34 +99,19 @@ __device__ __forceinline__ void knn_insert(unsigned long long (&keys)[SLOTS], un
     m &= m - 1;
     const unsigned long long ck = shfl64(key, b);
     if (ck < thresh) {
-      // locate the current maximum of the set, replace it, recompute the threshold
-      unsigned long long lmax = keys[0];
-      int lslot = 0;
+      int lslot = -1;
 #pragma unroll
-      for (int s = 1; s < SLOTS; ++s)
-        if (keys[s] > lmax) { lmax = keys[s]; lslot = s; }
-      unsigned long long wmax = lmax;
+      for (int s = SLOTS - 1; s >= 0; --s)
+        if (keys[s] == thresh) lslot = s;
+      const int owner = __ffs(__ballot_sync(0xffffffffu, lslot >= 0)) - 1;   // several lanes may hold a KEY_INF placeholder
+      unsigned long long lmax = 0ull;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long t = shfl_xor64(wmax, o);
-        wmax = t > wmax ? t : wmax;
+      for (int s = 0; s < SLOTS; ++s) {
+        if (lane == owner && s == lslot) keys[s] = ck;
+        lmax = keys[s] > lmax ? keys[s] : lmax;
       }
-      const int owner = __ffs(__ballot_sync(0xffffffffu, lmax == wmax)) - 1;
-      if (lane == owner) {
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s)
-          if (s == lslot) keys[s] = ck;
-      }
-      lmax = keys[0];
-#pragma unroll
-      for (int s = 1; s < SLOTS; ++s) lmax = keys[s] > lmax ? keys[s] : lmax;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long t = shfl_xor64(lmax, o);
-        lmax = t > lmax ? t : lmax;
-      }
-      thresh = lmax;
-      thr_hi = (unsigned)(lmax >> 32);
+      thresh = warp_max64(lmax);
+      thr_hi = (unsigned)(thresh >> 32);
     }
   }
 }
@@ -188,11 +183,17 @@ knn_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, int64
           pass = pass || da[qi] <= thr_hi[qi] || db[qi] <= thr_hi[qi];
         }
         if (!__any_sync(0xffffffffu, pass)) continue;
+        // which (query, half) pairs have a survivor: one OR-reduction of a per-lane bit mask instead of 2*QW votes
+        unsigned bits = 0;
+#pragma unroll
+        for (int qi = 0; qi < QW; ++qi)
+          bits |= (da[qi] <= thr_hi[qi] ? (1u << qi) : 0u) | (db[qi] <= thr_hi[qi] ? (1u << (QW + qi)) : 0u);
+        const unsigned any = __reduce_or_sync(0xffffffffu, bits);
 #pragma unroll
         for (int qi = 0; qi < QW; ++qi) {
-          if (__ballot_sync(0xffffffffu, da[qi] <= thr_hi[qi]))
+          if (any & (1u << qi))
             knn_insert<SLOTS>(keys[qi], thresh[qi], thr_hi[qi], ((unsigned long long)da[qi] << 32) | (unsigned)ca, lane);
-          if (__ballot_sync(0xffffffffu, db[qi] <= thr_hi[qi]))
+          if (any & (1u << (QW + qi)))
             knn_insert<SLOTS>(keys[qi], thresh[qi], thr_hi[qi], ((unsigned long long)db[qi] << 32) | (unsigned)cb, lane);
         }
       } else {
