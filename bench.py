@@ -487,6 +487,9 @@ def run_mesh_c4(args):
     sampler.start()
     knn_ms = _ev_time(lambda: dc.knn_graph(pos, k), max(2, args.steps // 2), 1)
     ei = dc.knn_graph(pos, k)
+    radius = (3.0 * k / (4.0 * 3.141592653589793 * N)) ** (1.0 / 3.0)   # ~k neighbours per point at this density
+    radius_ms = _ev_time(lambda: dc.radius_graph(pos, radius), max(2, args.steps // 2), 1)
+    radius_edges = dc.radius_graph(pos, radius).shape[1]
     x0 = dc.to_log_freq(pos)
 
     def fwd():
@@ -509,6 +512,8 @@ def run_mesh_c4(args):
                                  "l2": "features 205 MB per layer vs 126 MB L2"},
                       "clocks": clocks, "gpu_launches": int(launches), "knn_build_ms": knn_ms,
                       "knn_pair_distances_per_sec": N * N / (knn_ms * 1e-3), "mp_15_layers_ms": mp_ms,
+                      "radius_build_ms": radius_ms, "radius": radius, "radius_edges": int(radius_edges),
+                      "radius_pair_distances_per_sec": N * N / (radius_ms * 1e-3),
                       "edge_traversals_per_sec": 3 * L * E / (mp_ms * 1e-3)}), flush=True)
 
 

@@ -16,8 +16,8 @@ using namespace dcb;
 
 constexpr int KNN_THREADS = 256;
 constexpr int KNN_WARPS = KNN_THREADS / 32;
-constexpr int QPW = 4;
-constexpr int QPB = KNN_WARPS * QPW;  // queries per block
+constexpr int RQW = 8;                  // radius search: queries per warp
+constexpr int RQB = KNN_WARPS * RQW;   // ... per block
 constexpr int TILE = 1024;
 constexpr unsigned long long KEY_INF = ~0ull;
 
@@ -251,23 +251,26 @@ radius_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, in
               int loop, int W, int32_t* __restrict__ out, int32_t* __restrict__ count_out) {
   __shared__ float sx[TILE], sy[TILE], sz[TILE];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t qb0 = (int64_t)blockIdx.x * QPB;
-  const int64_t qb1 = min(N, qb0 + QPB) - 1;
+  const int64_t qb0 = (int64_t)blockIdx.x * RQB;
+  const int64_t qb1 = min(N, qb0 + RQB) - 1;
   const int64_t cand_lo = ptr[find_graph(ptr, B, qb0)];
   const int64_t cand_hi = ptr[find_graph(ptr, B, qb1) + 1];
-  float qx[QPW], qy[QPW], qz[QPW];
-  int64_t lo[QPW], hi[QPW];
-  bool qv[QPW];
-  int cnt[QPW];
+  float qx[RQW], qy[RQW], qz[RQW];
+  int64_t lo[RQW], hi[RQW];
+  bool qv[RQW];
+  int cnt[RQW];
+  float r2q[RQW];   // the radius test of a query that is full is switched off (-1)
 #pragma unroll
-  for (int qi = 0; qi < QPW; ++qi) {
-    const int64_t q = qb0 + warp * QPW + qi;
+  for (int qi = 0; qi < RQW; ++qi) {
+    const int64_t q = qb0 + warp * RQW + qi;
     qv[qi] = q < N;
     const int64_t qq = qv[qi] ? q : (N - 1);
     const int g = find_graph(ptr, B, qq);
     lo[qi] = ptr[g]; hi[qi] = ptr[g + 1];
-    qx[qi] = pos[3 * qq]; qy[qi] = pos[3 * qq + 1]; qz[qi] = pos[3 * qq + 2];
+    const float nan = __int_as_float(0x7fc00000);
+    qx[qi] = qv[qi] ? pos[3 * qq] : nan; qy[qi] = qv[qi] ? pos[3 * qq + 1] : nan; qz[qi] = qv[qi] ? pos[3 * qq + 2] : nan;
     cnt[qi] = 0;
+    r2q[qi] = r2;
   }
   for (int64_t t0 = cand_lo; t0 < cand_hi; t0 += TILE) {
     __syncthreads();
@@ -277,24 +280,52 @@ radius_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, in
       sx[i] = pos[3 * c]; sy[i] = pos[3 * c + 1]; sz[i] = pos[3 * c + 2];
     }
     __syncthreads();
-    bool all_full = true;
+    bool all_full = true, all_inside = true;
 #pragma unroll
-    for (int qi = 0; qi < QPW; ++qi) all_full = all_full && (!qv[qi] || cnt[qi] >= cap);
+    for (int qi = 0; qi < RQW; ++qi) {
+      all_full = all_full && (!qv[qi] || cnt[qi] >= cap);
+      all_inside = all_inside && (!qv[qi] || (t0 >= lo[qi] && t0 + tile_n <= hi[qi]));
+    }
     if (all_full) continue;  // still takes part in the tile loads above
-    for (int j0 = 0; j0 < tile_n; j0 += 32) {
-      const int j = j0 + lane;
-      const bool inb = j < tile_n;
-      const float px = inb ? sx[j] : 0.f, py = inb ? sy[j] : 0.f, pz = inb ? sz[j] : 0.f;
-      const int64_t c = t0 + j;
+    for (int j0 = 0; j0 < tile_n; j0 += 64) {
+      // two candidates per lane, 2*RQW vote-free distance chains, then one warp vote (hits are rare for a small radius);
+      // TILE is a multiple of 64, so both reads stay inside the arrays (stale values past tile_n are masked)
+      const int ja = j0 + lane, jb = ja + 32;
+      const float pxa = sx[ja], pya = sy[ja], pza = sz[ja];
+      const float pxb = sx[jb], pyb = sy[jb], pzb = sz[jb];
+      const int64_t ca = t0 + ja, cb = t0 + jb;
+      const bool fast = all_inside && j0 + 64 <= tile_n;
+      const bool inba = ja < tile_n, inbb = jb < tile_n;
+      bool ha[RQW], hb[RQW];
+      bool pass = false;
+      if (fast) {   // whole step inside every query's own point cloud: nothing but the distance tests
 #pragma unroll
-      for (int qi = 0; qi < QPW; ++qi) {
-        const float d = sqdist(qx[qi], qy[qi], qz[qi], px, py, pz);
-        const bool hit = inb && qv[qi] && c >= lo[qi] && c < hi[qi] && d < r2;
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (m && cnt[qi] < cap) {
-          const int p = cnt[qi] + __popc(m & ((1u << lane) - 1u));
-          if (hit && p < cap) out[(qb0 + warp * QPW + qi) * W + p] = (int32_t)c;
-          cnt[qi] = min(cap, cnt[qi] + __popc(m));
+        for (int qi = 0; qi < RQW; ++qi) {
+          ha[qi] = sqdist(qx[qi], qy[qi], qz[qi], pxa, pya, pza) < r2q[qi];   // NaN for an invalid query: never a hit
+          hb[qi] = sqdist(qx[qi], qy[qi], qz[qi], pxb, pyb, pzb) < r2q[qi];
+          pass = pass || ha[qi] || hb[qi];
+        }
+      } else {
+#pragma unroll
+        for (int qi = 0; qi < RQW; ++qi) {
+          ha[qi] = inba && ca >= lo[qi] && ca < hi[qi] && sqdist(qx[qi], qy[qi], qz[qi], pxa, pya, pza) < r2q[qi];
+          hb[qi] = inbb && cb >= lo[qi] && cb < hi[qi] && sqdist(qx[qi], qy[qi], qz[qi], pxb, pyb, pzb) < r2q[qi];
+          pass = pass || ha[qi] || hb[qi];
+        }
+      }
+      if (!__any_sync(0xffffffffu, pass)) continue;
+#pragma unroll
+      for (int qi = 0; qi < RQW; ++qi) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {   // ascending candidate index: first the lower 32, then the upper 32
+          const bool hit = half ? hb[qi] : ha[qi];
+          const unsigned m = __ballot_sync(0xffffffffu, hit);
+          if (m) {
+            const int p = cnt[qi] + __popc(m & ((1u << lane) - 1u));
+            if (hit && p < cap) out[(qb0 + warp * RQW + qi) * W + p] = (int32_t)(half ? cb : ca);
+            cnt[qi] = min(cap, cnt[qi] + __popc(m));
+            if (cnt[qi] >= cap) r2q[qi] = -1.f;   // full: no further candidate can hit (hits past `cap` are dropped above)
+          }
         }
       }
     }
@@ -302,8 +333,8 @@ radius_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, in
   __syncwarp();
   // drop the self match (if it made it into the first `cap` hits), pad with -1
 #pragma unroll
-  for (int qi = 0; qi < QPW; ++qi) {
-    const int64_t q = qb0 + warp * QPW + qi;
+  for (int qi = 0; qi < RQW; ++qi) {
+    const int64_t q = qb0 + warp * RQW + qi;
     if (!qv[qi]) continue;
     int32_t* row = out + q * W;
     const int n = cnt[qi];
@@ -378,7 +409,7 @@ extern "C" int dc_radius(const float* pos, const int64_t* ptr, int64_t B, int64_
   DC_REQUIRE(pos && ptr && nbr_out, DC_EINVAL, "radius: null pointer");
   const int cap = max_nbr + (loop ? 0 : 1);
   const float r2 = r * r;  // fp32 product, as torch_cluster
-  radius_kernel<<<(unsigned)cdiv(N, QPB), KNN_THREADS, 0, st>>>(pos, ptr, B, N, r2, cap, loop, cap, nbr_out, count_out);
+  radius_kernel<<<(unsigned)cdiv(N, RQB), KNN_THREADS, 0, st>>>(pos, ptr, B, N, r2, cap, loop, cap, nbr_out, count_out);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

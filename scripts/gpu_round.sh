@@ -13,6 +13,7 @@ for f in ('bench_default','bench_reference','bench_c2','bench_c4','bench_c5'):
     d=json.load(open('gpurun_out/%s.json'%f)); print(f, d['metric'], round(d['value'],2), d.get('e2e') and round(d['e2e']['value'],1), d.get('roofline') and round(d['roofline']['frac'],3), d.get('gpu_launches'), round(d['ms_per_step'],2))
 "
 python scripts/gemm_lab.py > gpurun_out/gemm_lab.txt 2>&1
+timeout 300 python scripts/k1_chain_lab.py --out gpurun_out/k1_chain_lab.json > gpurun_out/k1_chain_lab.txt 2>&1; cat gpurun_out/k1_chain_lab.txt
 python scripts/step_profile.py > gpurun_out/step_profile.txt 2>&1; tail -30 gpurun_out/step_profile.txt | head -14
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 90000 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_under_ncu.log 2>&1

@@ -14,7 +14,7 @@ ends = [i for i, r in enumerate(rows) if "FusedAdam" in r["Kernel Name"]]   # on
 last = rows[ends[-2] + 1: ends[-1] + 1] if len(ends) >= 2 else rows
 OURS = ("dcb::", "spmm_", "blk_", "rs_", "csr_", "softmax_", "colsum", "relu_bwd", "knn", "pack_edges", "edge_weights", "deg_inv",
         "make_keys", "scan_", "t2_reduce", "gemm_tc2", "sgemm_kernel", "splitk", "mesh_", "posenc", "gat_", "segment_sum", "edge_relu",
-        "rowptr", "nbr_")
+        "rowptr", "nbr_", "rowdot", "edge_loss", "batch_vector", "edges_offset", "node_features", "instance_points")
 agg = collections.defaultdict(lambda: [0, 0.0])
 for r in last:
     v = float(r["Metric Value"].replace(",", ""))
