@@ -10,7 +10,22 @@ for backbone in ("TAGConv", "GCNConv", "GATConv", "MPNN"):
     loss, _, _ = dc.train_step_loss(m, rest, rigid, deformed)
     loss.backward()
 pos = torch.rand(700, 3, device="cuda")
-dc.knn_graph(pos, 40); dc.radius_graph(pos, 0.2)
+ptr3 = torch.tensor([0, 100, 100, 700], device="cuda")
+dc.knn_graph(pos, 40); dc.knn_graph(pos, 16); dc.knn_graph(pos, 70, loop=True); dc.knn_graph(pos, 8, ptr=ptr3)
+dc.radius_graph(pos, 0.2); dc.radius_graph(pos, 0.3, ptr=ptr3, max_num_neighbors=5)
+# N3 batch assembly: every entry point, ragged inputs, int32 and int64 local indices
+parts = [rest[i] for i in range(2)]
+cpu = lambda t: t.cpu()
+dc.batch_from_data_list([dc.Data(x=cpu(p.x), edge_index=cpu(p.edge_index), pos=cpu(p.pos)) for p in parts])
+dc.graph_batch([cpu(p.pos) for p in parts], [cpu(p.edge_index).int() for p in parts])
+sv, st = synthetic.uv_sphere()
+dc.mesh_batch([sv.numpy(), sv[:400].numpy()], [st.int().numpy(), st[st.max(1).values < 400].numpy()])
+dc.collider_batch(torch.rand(3, 3, dtype=torch.float64), torch.randn(3, 3), torch.rand(3))
+# K1 v9 hop chain: forward into a strided buffer and transposed in place, ragged tiles
+gc = ops.GraphCSR(rest.edge_index, rest.x.shape[0], "tag", rest._ptr_host)
+hx = torch.randn(rest.x.shape[0], 64, device="cuda"); hb = torch.zeros(rest.x.shape[0], 192, device="cuda")
+ops.propagate_chain(gc, [(hx, None, hb[:, :64]), (hb[:, :64], None, hb[:, 64:128]), (hb[:, 64:128], None, hb[:, 128:])])
+ops.propagate_chain(gc, [(hx, hb[:, :64], hb[:, :64]), (hb[:, :64], hb[:, 64:128], hb[:, 64:128])], transpose=True)
 x = torch.randn(rest.x.shape[0], 256, device="cuda", requires_grad=True)
 for variant in ("generic", "tiled", "tiled8", "tiled_prefetch", "smem", "lean", "blocks", "auto"):
     ops.K1_VARIANT = variant
