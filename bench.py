@@ -38,6 +38,12 @@ METRIC = "train_step_graphs_per_sec"
 K1_NCU_TRAFFIC_RATIO = 1040.28 / 1069.80
 K1_NCU_TRAFFIC_SOURCE = ("profiles/r01_ncu_spmm_v6_lean.csv (C5 hop, N=512000, E=4096000, F=256): 560.5 MB read + 479.8 MB written "
                          "per launch, scaled by this launch's algorithmic bytes")
+# the same for a 3-hop chain launch (K1 v9): 624.4 MB read + 1538.6 MB written vs 3 x 1069.8 MB algorithmic (hops 2 and 3 read
+# rows that are still in L2)
+K1_CHAIN_NCU_TRAFFIC_RATIO = (624.36 + 1538.59) / (3 * 1069.80)
+K1_CHAIN_NCU_TRAFFIC_SOURCE = ("profiles/r01_ncu_spmm_v9_chain.csv (3-hop chain launch, C5 graph, F=256): 624.4 MB read + 1538.6 MB "
+                               "written per launch vs 3209 MB algorithmic; single-hop launches per r01_ncu_spmm_v6_lean.csv "
+                               "(1040 MB vs 1070 MB); scaled by each launch's algorithmic bytes")
 
 
 def parse():
@@ -249,12 +255,14 @@ def run_ours(args):
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     hop_bytes = hop_ms = 0.0
     hop_n = hop_hops = 0
+    hop_traffic = 0.0
     gemm_flops = gemm_ms = 0.0
     other = {}
     for rec in prof:
         ms = rec["e0"].elapsed_time(rec["e1"])
         if rec["op"] == "spmm" and rec["F"] == 256:
             hop_bytes += rec["bytes"]; hop_ms += ms; hop_n += 1; hop_hops += rec.get("hops", 1)
+            hop_traffic += rec["bytes"] * (K1_CHAIN_NCU_TRAFFIC_RATIO if rec.get("hops", 1) > 1 else K1_NCU_TRAFFIC_RATIO)
         elif rec["op"] == "gemm":
             gemm_flops += rec["flops"]; gemm_ms += ms
         other[rec["op"]] = other.get(rec["op"], 0.0) + ms
@@ -263,7 +271,7 @@ def run_ours(args):
         ach = hop_bytes / (hop_ms * 1e-3) / 1e9
         roofline = {"kernel": f"K1 gather/segmented-sum hop, F=256 ({ops.K1_VARIANT} variant)", "bound": "hbm",
                     "achieved": ach, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": K1_NCU_TRAFFIC_RATIO * hop_bytes / hop_n, "traffic_source": K1_NCU_TRAFFIC_SOURCE,
+                    "traffic": hop_traffic / hop_n, "traffic_source": K1_CHAIN_NCU_TRAFFIC_SOURCE,
                     "launches": hop_n // args.steps, "hops": hop_hops // args.steps, "avg_launch_ms": hop_ms / hop_n,
                     "avg_hop_ms": hop_ms / hop_hops,
                     "algorithmic_bytes_per_launch": hop_bytes / hop_n,
@@ -392,6 +400,10 @@ def run_layer(args):
     hop_ms = ev_time(lambda: G.propagate(x, out=out), args.steps)
     hop_v1_ms = ev_time(lambda: ops.spmm(G.rowptr, G.nbr, x, dis=G.dis, out=out), args.steps)
     hop_t_ms = ev_time(lambda: G.propagate(x, transpose=True, out=out), args.steps)
+    cbuf = torch.empty((N, 3 * F), device=dev)
+    cv = [x] + [cbuf[:, i * F:(i + 1) * F] for i in range(3)]
+    chain_ms = ev_time(lambda: ops.propagate_chain(G, [(cv[i], None, cv[i + 1]) for i in range(3)]), args.steps)   # what a TAGConv layer runs
+    del cbuf, cv
     xg = x.clone().requires_grad_(True)
     gin = G if args.layer == "tag" else ei
     fwd_ms = ev_time(lambda: layer(x, gin, relu=True), args.steps)
@@ -405,7 +417,8 @@ def run_layer(args):
     launches = (dc._abi.lib().dc_launch_count() - l0) // (args.steps + max(args.warmup, 3))
     clocks = sampler.stop()
     hop_bytes = 8 * N * F + 4 * E + 8 * N + 4
-    ach = hop_bytes / (hop_ms * 1e-3) / 1e9
+    chained = ops.K1_CHAIN >= 1 and G.tiles_closed and F % 32 == 0
+    ach = (3 * hop_bytes / (chain_ms * 1e-3) / 1e9) if chained else (hop_bytes / (hop_ms * 1e-3) / 1e9)
     line = {"metric": "mp_layer_edges_per_sec", "value": E / (fb_ms * 1e-3), "unit": "edges/s", "n_gpus": 1,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": fb_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
@@ -414,10 +427,16 @@ def run_layer(args):
             "clocks": clocks, "gpu_launches": int(launches),
             "fwd_ms": fwd_ms, "fwd_edges_per_sec": E / (fwd_ms * 1e-3),
             "edge_traversals_per_sec_fwd_bwd": 6 * E / (fb_ms * 1e-3),
-            "hop": {"fwd_ms": hop_ms, "transpose_ms": hop_t_ms, "generic_v1_ms": hop_v1_ms, "edges_per_sec": E / (hop_ms * 1e-3)},
-            "roofline": {"kernel": f"K1 hop ({ops.K1_VARIANT})", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": peak_src,
-                         "unit": "GB/s", "frac": ach / hbm_peak, "traffic": K1_NCU_TRAFFIC_RATIO * hop_bytes,
-                         "traffic_source": K1_NCU_TRAFFIC_SOURCE, "algorithmic_bytes_per_launch": hop_bytes}}
+            "hop": {"fwd_ms": hop_ms, "transpose_ms": hop_t_ms, "generic_v1_ms": hop_v1_ms, "edges_per_sec": E / (hop_ms * 1e-3),
+                    "chain3_ms": chain_ms, "chain3_ms_per_hop": chain_ms / 3, "single_hop_frac": hop_bytes / (hop_ms * 1e-3) / 1e9 / hbm_peak},
+            "roofline": {"kernel": (f"K1 v9 hop chain: the 3 forward hops of the layer in one launch ({ops.K1_VARIANT})" if chained
+                                    else f"K1 hop ({ops.K1_VARIANT})"),
+                         "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": ach / hbm_peak,
+                         "traffic": (K1_CHAIN_NCU_TRAFFIC_RATIO * 3 * hop_bytes) if chained else (K1_NCU_TRAFFIC_RATIO * hop_bytes),
+                         "traffic_source": K1_CHAIN_NCU_TRAFFIC_SOURCE if chained else K1_NCU_TRAFFIC_SOURCE,
+                         "algorithmic_bytes_per_launch": (3 if chained else 1) * hop_bytes,
+                         "avg_launch_ms": chain_ms if chained else hop_ms}}
     print(json.dumps(line), flush=True)
 
 
