@@ -529,14 +529,32 @@ def _ptr_tensor(num_points, batch, ptr, device):
     return torch.cat([counts.new_zeros(1), counts.cumsum(0)]).to(_i64)
 
 
+# Neighbour search strategy: "auto" = uniform grid (K4g) for a single point cloud of at least KNN_GRID_MIN points,
+# tiled brute force (K4) otherwise; "brute" / "grid" force one (grid needs batch=None).  Results are bit-identical.
+KNN_MODE = os.environ.get("DCB200_KNN", "auto")
+KNN_GRID_MIN = 16384
+
+
+def _use_grid(N, batch, ptr, width):
+    single = batch is None and (ptr is None or ptr.numel() == 2)
+    if KNN_MODE == "grid" and not single:
+        raise _abi.DcError("DCB200_KNN=grid needs a single point cloud (batch=None)")
+    return single and width <= 128 and (KNN_MODE == "grid" or (KNN_MODE == "auto" and N >= KNN_GRID_MIN))
+
+
 def knn_table(pos, k, batch=None, ptr=None, loop=False):
     """int32 [N, k (+1 if not loop)] neighbour table, ascending (distance, index), -1 padded."""
     _need(pos, _f32, "pos")
     pos = pos.contiguous()
     N = pos.shape[0]
-    p = _ptr_tensor(N, batch, ptr, pos.device)
     W = k + (0 if loop else 1)
     tab = torch.empty((N, W), dtype=_i32, device=pos.device)
+    if _use_grid(N, batch, ptr, W):
+        nb = _abi.lib().dc_knn_grid_workspace_bytes(N)
+        ws = _workspace(nb, pos.device)
+        _abi.call("dc_knn_grid", _ptr(pos), N, k, int(bool(loop)), _ptr(tab), _ptr(ws), nb, _stream())
+        return tab
+    p = _ptr_tensor(N, batch, ptr, pos.device)
     _abi.call("dc_knn", _ptr(pos), _ptr(p), p.numel() - 1, N, k, int(bool(loop)), _ptr(tab), _stream())
     return tab
 
@@ -545,10 +563,16 @@ def radius_table(pos, r, batch=None, ptr=None, loop=False, max_num_neighbors=32)
     _need(pos, _f32, "pos")
     pos = pos.contiguous()
     N = pos.shape[0]
-    p = _ptr_tensor(N, batch, ptr, pos.device)
     W = max_num_neighbors + (0 if loop else 1)
     tab = torch.empty((N, W), dtype=_i32, device=pos.device)
     cnt = torch.empty(N, dtype=_i32, device=pos.device)
+    if _use_grid(N, batch, ptr, W):
+        nb = _abi.lib().dc_knn_grid_workspace_bytes(N)
+        ws = _workspace(nb, pos.device)
+        _abi.call("dc_radius_grid", _ptr(pos), N, float(r), max_num_neighbors, int(bool(loop)), _ptr(tab), _ptr(cnt), _ptr(ws), nb,
+                  _stream())
+        return tab, cnt
+    p = _ptr_tensor(N, batch, ptr, pos.device)
     _abi.call("dc_radius", _ptr(pos), _ptr(p), p.numel() - 1, N, float(r), max_num_neighbors, int(bool(loop)), _ptr(tab),
               _ptr(cnt), _stream())
     return tab, cnt

@@ -259,6 +259,15 @@ DC_API int dc_knn(const float* pos /*[N,3]*/, const int64_t* ptr, int64_t num_gr
            int loop, int32_t* nbr_out, dc_stream_t stream);
 DC_API int dc_radius(const float* pos, const int64_t* ptr, int64_t num_graphs, int64_t num_points, float r,
               int32_t max_nbr, int loop, int32_t* nbr_out, int32_t* count_out, dc_stream_t stream);
+/* K4g: the same searches for ONE point cloud (batch=None) on a uniform grid: bounding box, ~8 points per cell,
+ * counting sort by cell, one warp per query walking rings of cells until the answer is provably complete.  Results
+ * are bit-identical to dc_knn / dc_radius (same distances, keys and tie rule; radius keeps the lowest indices).  All
+ * grid parameters are computed on the device (no host sync).  Worth it from a few ten thousand points up. */
+DC_API size_t dc_knn_grid_workspace_bytes(int64_t num_points);
+DC_API int dc_knn_grid(const float* pos, int64_t num_points, int32_t k, int loop, int32_t* nbr_out, void* workspace,
+                size_t workspace_bytes, dc_stream_t stream);
+DC_API int dc_radius_grid(const float* pos, int64_t num_points, float r, int32_t max_nbr, int loop, int32_t* nbr_out,
+                   int32_t* count_out, void* workspace, size_t workspace_bytes, dc_stream_t stream);
 /* Compacts a padded neighbour table into edge_index int64 [2, E_cap] (row 0 = neighbour,
  * row 1 = query), queries ascending; *num_edges_out (device int64) receives E. */
 DC_API size_t dc_nbr_to_edge_index_workspace_bytes(int64_t num_points);

@@ -13,6 +13,10 @@ pos = torch.rand(700, 3, device="cuda")
 ptr3 = torch.tensor([0, 100, 100, 700], device="cuda")
 dc.knn_graph(pos, 40); dc.knn_graph(pos, 16); dc.knn_graph(pos, 70, loop=True); dc.knn_graph(pos, 8, ptr=ptr3)
 dc.radius_graph(pos, 0.2); dc.radius_graph(pos, 0.3, ptr=ptr3, max_num_neighbors=5)
+ops.KNN_MODE = "grid"   # K4g: uniform-grid search (bounding box, counting sort, ring walk), kNN and radius
+dc.knn_graph(pos, 16); dc.knn_graph(pos, 70, loop=True); dc.radius_graph(pos, 0.2); dc.radius_graph(pos, 0.3, max_num_neighbors=5)
+dc.knn_graph(torch.full((50, 3), 0.5, device="cuda"), 4)
+ops.KNN_MODE = "auto"
 # N3 batch assembly: every entry point, ragged inputs, int32 and int64 local indices
 parts = [rest[i] for i in range(2)]
 cpu = lambda t: t.cpu()

@@ -429,3 +429,66 @@ def test_hop_chain_rejects_bad_args(dc):
     x = torch.randn(100, 32).cuda()
     with pytest.raises(_abi.DcError):      # in aliases out
         ops.spmm_chain(g.rowptr, g.edges, None, [(x, None, x)], tile_ptr=g.tile_ptr, n_tiles=g.n_tiles)
+
+
+def _clouds():
+    g = torch.Generator().manual_seed(77)
+    uni = torch.rand(6000, 3, generator=g) - 0.5
+    clustered = torch.cat([0.01 * torch.randn(2500, 3, generator=g) + 0.3, 0.02 * torch.randn(2500, 3, generator=g) - 0.2,
+                           torch.rand(300, 3, generator=g)])
+    dup = torch.rand(700, 3, generator=g)
+    dup = torch.cat([dup, dup[:400], dup[:100]])               # exact duplicates: ties on the distance -> lower index wins
+    planar = torch.cat([torch.rand(4000, 2, generator=g), torch.zeros(4000, 1)], 1)
+    lattice = torch.stack(torch.meshgrid(*[torch.arange(16.0)] * 3, indexing="ij"), -1).reshape(-1, 3) * 0.25   # massive ties
+    same = torch.full((300, 3), 0.125)
+    shifted = torch.rand(3000, 3, generator=g) * 1e-3 + 100.0   # tiny extent far from the origin (coarse fp32 grid)
+    return dict(uniform=uni, clustered=clustered, duplicates=dup, planar=planar, lattice=lattice, coincident=same, shifted=shifted)
+
+
+@pytest.mark.parametrize("name", ["uniform", "clustered", "duplicates", "planar", "lattice", "coincident", "shifted"])
+def test_grid_search_bit_identical_to_brute_force(dc, name):
+    """K4g (uniform grid) == K4 (tiled brute force) bit for bit: neighbour tables incl. order, for kNN (several k, loop)
+    and radius search (incl. truncation to the lowest indices), on uniform / clustered / degenerate clouds."""
+    from deformcontact_b200 import ops
+    pos = _clouds()[name].cuda()
+    ext = float((pos.max(0).values - pos.min(0).values).max())
+    try:
+        for k, loop in ((16, False), (8, True), (40, False), (100, False)):
+            ops.KNN_MODE = "brute"
+            ref = ops.knn_table(pos, k, loop=loop)
+            ops.KNN_MODE = "grid"
+            out = ops.knn_table(pos, k, loop=loop)
+            assert torch.equal(out, ref), f"knn {name} k={k} loop={loop}: {(out != ref).sum().item()} entries differ"
+        for r, mx, loop in ((0.05 * ext + 1e-6, 32, False), (0.2 * ext + 1e-6, 5, False), (0.1 * ext + 1e-6, 64, True), (0.0, 8, False)):
+            ops.KNN_MODE = "brute"
+            ref, rc = ops.radius_table(pos, r, loop=loop, max_num_neighbors=mx)
+            ops.KNN_MODE = "grid"
+            out, oc = ops.radius_table(pos, r, loop=loop, max_num_neighbors=mx)
+            assert torch.equal(out, ref) and torch.equal(oc, rc), f"radius {name} r={r} max={mx} loop={loop}"
+    finally:
+        ops.KNN_MODE = "auto"
+
+
+def test_grid_search_large_cloud_vs_oracle_and_auto_dispatch(dc):
+    """Above KNN_GRID_MIN points a single cloud goes to the grid automatically; edge_index equals the oracle's on a sample
+    of queries (the oracle is O(N^2): checked per query against its brute-force definition) and the brute-force kernel's."""
+    from deformcontact_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    pos = torch.rand(40000, 3, generator=g)
+    assert ops._use_grid(pos.shape[0], None, None, 17)
+    ei = dc.knn_graph(pos.cuda(), 16)
+    ops.KNN_MODE = "brute"
+    try:
+        ref = dc.knn_graph(pos.cuda(), 16)
+    finally:
+        ops.KNN_MODE = "auto"
+    assert torch.equal(ei, ref)
+    sub = torch.arange(0, 40000, 997)
+    d = ((pos[sub, None, :] - pos[None, :, :]) ** 2)
+    d2 = (d[..., 0] + d[..., 1]) + d[..., 2]                      # the oracle's association (oracle/graphs.py:_sqdist)
+    d2[torch.arange(sub.numel()), sub] = float("inf")
+    want = torch.topk(d2, 16, dim=1, largest=False).indices.sort(1).values
+    tab = ei[0].cpu().reshape(40000, 16)[sub].sort(1).values
+    assert torch.equal(tab, want)
+    # batched clouds never take the grid path
+    assert not ops._use_grid(40000, torch.zeros(40000, dtype=torch.long), None, 17)
