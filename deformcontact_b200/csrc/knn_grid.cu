@@ -267,9 +267,17 @@ int build_grid(const float* pos, int64_t N, const GridWs& g, cudaStream_t st) {
 }
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256)
+extract_order_kernel(const float4* __restrict__ sorted, int64_t N, int32_t* __restrict__ order) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < N) order[i] = __float_as_int(sorted[i].w);
+}
+}  // namespace
+
 extern "C" size_t dc_knn_grid_workspace_bytes(int64_t N) { return carve_grid(nullptr, N > 0 ? N : 1).bytes; }
 
-extern "C" int dc_knn_grid(const float* pos, int64_t N, int32_t k, int loop, int32_t* nbr_out, void* workspace,
+extern "C" int dc_knn_grid(const float* pos, int64_t N, int32_t k, int loop, int32_t* nbr_out, int32_t* order_out, void* workspace,
                            size_t workspace_bytes, dc_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   DC_REQUIRE(N >= 0 && k >= 1, DC_EINVAL, "knn_grid: bad sizes N=%lld k=%d", (long long)N, k);
@@ -286,11 +294,15 @@ extern "C" int dc_knn_grid(const float* pos, int64_t N, int32_t k, int loop, int
   else if (kk <= 64) grid_search_kernel<2, 0><<<grid, GRID_THREADS, 0, st>>>(g.sorted, g.count, g.gp, N, kk, loop, kk, 0.f, nbr_out, nullptr);
   else grid_search_kernel<4, 0><<<grid, GRID_THREADS, 0, st>>>(g.sorted, g.count, g.gp, N, kk, loop, kk, 0.f, nbr_out, nullptr);
   DC_LAUNCH_CHECK();
+  if (order_out) {
+    extract_order_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(g.sorted, N, order_out);
+    DC_LAUNCH_CHECK();
+  }
   return DC_OK;
 }
 
 extern "C" int dc_radius_grid(const float* pos, int64_t N, float r, int32_t max_nbr, int loop, int32_t* nbr_out,
-                              int32_t* count_out, void* workspace, size_t workspace_bytes, dc_stream_t stream_) {
+                              int32_t* count_out, int32_t* order_out, void* workspace, size_t workspace_bytes, dc_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   DC_REQUIRE(N >= 0 && max_nbr >= 1, DC_EINVAL, "radius_grid: bad sizes");
   if (N == 0) return DC_OK;
@@ -306,6 +318,25 @@ extern "C" int dc_radius_grid(const float* pos, int64_t N, float r, int32_t max_
   if (cap <= 32) grid_search_kernel<1, 1><<<grid, GRID_THREADS, 0, st>>>(g.sorted, g.count, g.gp, N, cap, loop, cap, r2, nbr_out, count_out);
   else if (cap <= 64) grid_search_kernel<2, 1><<<grid, GRID_THREADS, 0, st>>>(g.sorted, g.count, g.gp, N, cap, loop, cap, r2, nbr_out, count_out);
   else grid_search_kernel<4, 1><<<grid, GRID_THREADS, 0, st>>>(g.sorted, g.count, g.gp, N, cap, loop, cap, r2, nbr_out, count_out);
+  DC_LAUNCH_CHECK();
+  if (order_out) {
+    extract_order_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(g.sorted, N, order_out);
+    DC_LAUNCH_CHECK();
+  }
+  return DC_OK;
+}
+
+extern "C" int dc_cell_order(const float* pos, int64_t N, int32_t* order, void* workspace, size_t workspace_bytes,
+                             dc_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DC_REQUIRE(N >= 0, DC_EINVAL, "cell_order: negative size");
+  if (N == 0) return DC_OK;
+  DC_REQUIRE(pos && order && workspace, DC_EINVAL, "cell_order: null pointer");
+  DC_REQUIRE(N < (1ll << 31), DC_ENOSUP, "cell_order: N exceeds 32-bit indices");
+  const GridWs g = carve_grid(workspace, N);
+  DC_REQUIRE(workspace_bytes >= g.bytes, DC_EWORKSPACE, "cell_order: workspace too small");
+  if (int rc = build_grid(pos, N, g, st)) return rc;
+  extract_order_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(g.sorted, N, order);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

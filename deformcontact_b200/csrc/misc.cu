@@ -1,6 +1,7 @@
 // Small kernels around the message-passing layers: bias-gradient column sums, ReLU backward,
 // mesh -> edge list (utils/graph_utils.py:12-13), positional encoding (utils/pos_encoding.py:6-44)
 // and the GAT attention scalars (PyG gat_conv.py / utils/softmax.py).
+#include <algorithm>
 #include "common.cuh"
 
 namespace {
@@ -211,6 +212,47 @@ extern "C" int dc_relu_bwd(const float* Y, const float* dY, float* dX, int64_t n
     relu_bwd_kernel4<<<(unsigned)cdiv(n / 4, 256), 256, 0, st>>>((const float4*)Y, (const float4*)dY, (float4*)dX, n / 4);
   else
     relu_bwd_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(Y, dY, dX, n);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+namespace {
+// out[i, :] = in[perm[i], :]
+__global__ void __launch_bounds__(256)
+permute_rows_kernel4(const float4* __restrict__ in, int64_t ldin4, const int32_t* __restrict__ perm, float4* __restrict__ out,
+                     int64_t ldout4, int64_t N, int nvec) {
+  const int64_t total = N * nvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / nvec;
+    const int c = (int)(i - r * nvec);
+    out[r * ldout4 + c] = __ldg(in + (int64_t)perm[r] * ldin4 + c);
+  }
+}
+__global__ void __launch_bounds__(256)
+permute_rows_kernel1(const float* __restrict__ in, int64_t ldin, const int32_t* __restrict__ perm, float* __restrict__ out,
+                     int64_t ldout, int64_t N, int F) {
+  const int64_t total = N * F;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / F;
+    const int c = (int)(i - r * F);
+    out[r * ldout + c] = __ldg(in + (int64_t)perm[r] * ldin + c);
+  }
+}
+}  // namespace
+
+extern "C" int dc_permute_rows(const float* in, int64_t ldin, const int32_t* perm, float* out, int64_t ldout, int64_t N, int32_t F,
+                               dc_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DC_REQUIRE(N >= 0 && F >= 0, DC_EINVAL, "permute_rows: negative size");
+  if (N == 0 || F == 0) return DC_OK;
+  DC_REQUIRE(in && perm && out && in != out && ldin >= F && ldout >= F, DC_EINVAL, "permute_rows: bad args");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(N * (int64_t)F, 256 * 4), (int64_t)kSMs * 32);
+  if (F % 4 == 0 && ldin % 4 == 0 && ldout % 4 == 0 && al16(in) && al16(out))
+    permute_rows_kernel4<<<grid ? grid : 1, 256, 0, st>>>(reinterpret_cast<const float4*>(in), ldin / 4, perm,
+                                                          reinterpret_cast<float4*>(out), ldout / 4, N, F / 4);
+  else
+    permute_rows_kernel1<<<grid ? grid : 1, 256, 0, st>>>(in, ldin, perm, out, ldout, N, F);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

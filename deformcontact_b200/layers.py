@@ -74,14 +74,15 @@ class _TAGConvFn(torch.autograd.Function):
         N, Fi = x.shape
         K = len(weights) - 1
         Fo = weights[0].shape[0]
-        hs = [x]
+        hs = [g.to_internal(x)]        # a relabelled large graph (ops.REORDER) runs the whole layer in its own node order
         if K > 0:
             buf = torch.empty((N, K * Fi), dtype=x.dtype, device=x.device)
             for k in range(K):
                 hs.append(buf[:, k * Fi:(k + 1) * Fi])
-            ops.propagate_chain(g, [(hs[k], None, hs[k + 1]) for k in range(K)])   # h_{k+1} = A_hat h_k
+            ops.propagate_chain(g, [(hs[k], None, hs[k + 1]) for k in range(K)], internal=True)   # h_{k+1} = A_hat h_k
         out = ops.gemm([(h, w) for h, w in zip(hs, weights)], N, Fo, False, True, bias=bias, relu=relu,
                        precision=precision)
+        out = g.from_internal(out)
         ctx.g, ctx.relu, ctx.precision, ctx.has_bias = g, relu, precision, bias is not None
         ctx.save_for_backward(out if relu else None, *hs, *weights)
         return out
@@ -96,6 +97,7 @@ class _TAGConvFn(torch.autograd.Function):
         dout = dout.contiguous()
         if ctx.relu:
             dout = ops.relu_bwd(out, dout)
+        dout = g.to_internal(dout)     # hs are saved in the structure's node order
         N, Fo = dout.shape
         Fi = hs[0].shape[1]
         need_x = ctx.needs_input_grad[0]
@@ -110,13 +112,13 @@ class _TAGConvFn(torch.autograd.Function):
             if ops.K1_CHAIN >= 2 and K > 0:
                 # all dH_k first, then the transposed hops as one chain, accumulating in place: dH_{k-1} += A_hat^T g_k
                 dhs = [ops.gemm([(dout, weights[k])], N, Fi, False, False, precision=ctx.precision) for k in range(K)] + [gk]
-                ops.propagate_chain(g, [(dhs[k + 1], dhs[k], dhs[k]) for k in range(K - 1, -1, -1)], transpose=True)
+                ops.propagate_chain(g, [(dhs[k + 1], dhs[k], dhs[k]) for k in range(K - 1, -1, -1)], transpose=True, internal=True)
                 gk = dhs[0]
             else:
                 for k in range(K - 1, -1, -1):
                     dhk = ops.gemm([(dout, weights[k])], N, Fi, False, False, precision=ctx.precision)
-                    gk = g.propagate(gk, transpose=True, add=dhk)
-            dx = gk
+                    gk = g.propagate(gk, transpose=True, add=dhk, internal=True)
+            dx = g.from_internal(gk)
         return (dx, None, db, None, None, *dws)
 
 

@@ -214,7 +214,8 @@ def fused_losses(pred, tgt):
     of train.py:47-58, computed by one libdcb200 kernel on the CSR pair the encoder built for ``pred.edge_index``."""
     from . import ops
     ptr = _host_ptr(pred) if getattr(pred, "ptr", None) is not None else None
-    g = ops.graph_csr(getattr(pred, "_structure_of", pred.edge_index), pred.pos.shape[0], "tag", ptr)
+    g = ops.graph_csr(getattr(pred, "_structure_of", pred.edge_index), pred.pos.shape[0], "tag", ptr,
+                      reorder=False)   # dc_edge_loss reads rowptr / nbr with the positions in their original order
     return _FusedLossFn.apply(pred.pos, tgt.pos, g)
 
 

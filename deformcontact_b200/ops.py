@@ -132,6 +132,61 @@ def make_tiles(ptr_host, num_nodes, target=TILE_NODES):
     return tiles
 
 
+# Node reordering for ONE large graph (no block-diagonal structure to tile by): the hops of a graph whose node order
+# is spatially random fetch every source row slice from L2 / DRAM.  When the edge builder knows the positions (knn_graph /
+# radius_graph on a single large cloud) it registers the grid-cell order of the points for the edge_index it returns; the
+# structure is then built on relabelled nodes and the layer runs its hops in that order (features permuted in and out,
+# dc_permute_rows).  Per-receiver sums keep their original edge order, so hop results are bit-identical.
+REORDER = os.environ.get("DCB200_REORDER", "1") != "0"
+REORDER_MIN_NODES = 32768
+_ORDER_HINTS = {}
+
+
+def _hint_key(edge_index):
+    return (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, edge_index.device.index)
+
+
+def register_order_hint(edge_index, order):
+    """``order`` int32 [N]: a spatially coherent permutation of the nodes (new position -> node id) for this edge_index."""
+    if len(_ORDER_HINTS) >= 8:
+        _ORDER_HINTS.pop(next(iter(_ORDER_HINTS)))
+    _ORDER_HINTS[_hint_key(edge_index)] = (edge_index, order)   # the entry pins the tensor so its address cannot be recycled
+
+
+def _order_hint(edge_index, num_nodes):
+    hit = _ORDER_HINTS.get(_hint_key(edge_index))
+    return hit[1] if hit is not None and hit[1].numel() == num_nodes else None
+
+
+def _eligible_order(edge_index, num_nodes, mode, ptr_host):
+    """The registered spatial order if this structure qualifies for relabelling (one large TAG/GCN graph), else None."""
+    if not (REORDER and mode in ("tag", "gcn") and num_nodes >= REORDER_MIN_NODES and (ptr_host is None or len(ptr_host) <= 2)):
+        return None
+    return _order_hint(edge_index, num_nodes)
+
+
+def cell_order(pos):
+    """int32 [N]: point indices in grid-cell order (dc_cell_order)."""
+    _need(pos, _f32, "pos")
+    pos = pos.contiguous()
+    N = pos.shape[0]
+    order = torch.empty(N, dtype=_i32, device=pos.device)
+    nb = _abi.lib().dc_knn_grid_workspace_bytes(N)
+    ws = _workspace(nb, pos.device)
+    _abi.call("dc_cell_order", _ptr(pos), N, _ptr(order), _ptr(ws), nb, _stream())
+    return order
+
+
+def permute_rows(x, perm, out=None):
+    """out[i, :] = x[perm[i], :] (perm int32)."""
+    _need(x, _f32, "x"); _need(perm, _i32, "perm")
+    N, F = x.shape
+    if out is None:
+        out = torch.empty((N, F), dtype=_f32, device=x.device)
+    _abi.call("dc_permute_rows", _ptr(x), _rows(x, "x"), _ptr(perm), _ptr(out), _rows(out, "out"), N, F, _stream())
+    return out
+
+
 class GraphCSR:
     """Device-resident structure of one (batched) graph: CSR by target for the forward
     aggregation, CSR by source for its transpose (built lazily, used by backward), the
@@ -143,10 +198,18 @@ class GraphCSR:
     ``ptr_host`` (python list, ``Batch.ptr``) lets K1 align its tiles with graph boundaries.
     """
 
-    def __init__(self, edge_index, num_nodes, mode="tag", ptr_host=None):
+    def __init__(self, edge_index, num_nodes, mode="tag", ptr_host=None, reorder=True):
         if mode not in ("tag", "gcn", "gat", "plain"):
             raise ValueError(mode)
         self.mode, self.N, self.E = mode, int(num_nodes), int(edge_index.shape[1])
+        # one large graph with a registered spatial order: build everything on relabelled nodes (see REORDER above)
+        self.order = _eligible_order(edge_index, self.N, mode, ptr_host) if reorder else None
+        self.rank = None
+        if self.order is not None:
+            rank = torch.empty(self.N, dtype=_i64, device=edge_index.device)
+            rank[self.order.long()] = torch.arange(self.N, dtype=_i64, device=edge_index.device)
+            edge_index = rank[edge_index]                      # same edges, same order, new node labels
+            self.rank = rank.to(_i32)
         self.edge_index = edge_index
         self.self_loops = mode in ("gcn", "gat")
         self.rowptr, self.nbr, self.eid = csr_build(edge_index, self.N, 0, self.self_loops)
@@ -184,10 +247,23 @@ class GraphCSR:
                 self._edges_t = pack_edges(self._t[1], self._wt)
         return self._t
 
-    def propagate(self, h, transpose=False, add=None, out=None, bias=None, relu=False):
+    def to_internal(self, x):
+        """Rows of ``x`` in the structure's node order (identity unless the graph was relabelled)."""
+        return x if self.order is None else permute_rows(x, self.order)
+
+    def from_internal(self, y, out=None):
+        if self.order is None:
+            return y
+        return permute_rows(y, self.rank, out=out)
+
+    def propagate(self, h, transpose=False, add=None, out=None, bias=None, relu=False, internal=False):
         """out = act(add + A_hat h + bias) (A_hat^T when ``transpose``); A_hat per ``mode``.
         Uses the tiled L1-reuse kernel when the layout allows, else the generic kernel; both give
-        bit-identical results."""
+        bit-identical results.  ``internal``: operands are already in the structure's node order."""
+        if self.order is not None and not internal:
+            res = self.propagate(self.to_internal(h), transpose=transpose, add=None if add is None else self.to_internal(add),
+                                 bias=bias, relu=relu, internal=True)
+            return self.from_internal(res, out=out)
         rp, nb, _ = self.t if transpose else (self.rowptr, self.nbr, self.eid)
         w = self._wt if transpose else self.w
         self_loop = self.mode == "gcn"
@@ -208,15 +284,17 @@ def _al16(t):
     return t is None or (t.data_ptr() % 16 == 0)
 
 
-def propagate_chain(g, hops, transpose=False):
+def propagate_chain(g, hops, transpose=False, internal=False):
     """Consecutive hops of one layer: ``hops`` = [(in, add or None, out)], ``in`` of hop k normally the ``out`` of hop
     k-1.  One dc_spmm_chain launch when the structure allows it (block-diagonal batch with whole-graph tiles, F % 32 == 0,
     TAG/GCN weights), else one ``propagate`` per hop; both give bit-identical results."""
+    if g.order is not None and not internal:
+        return [g.propagate(h, transpose=transpose, add=a, out=o) for h, a, o in hops]
     F = hops[0][0].shape[1]
     ok = (K1_CHAIN and g.mode in ("tag", "gcn") and g.tiles_closed and F % 32 == 0 and len(hops) <= _abi.MAX_CHAIN
           and K1_VARIANT in ("auto", "lean", "blocks") and all(_tiled_ok(h, o, a, None) for h, a, o in hops))
     if not ok:
-        return [g.propagate(h, transpose=transpose, add=a, out=o) for h, a, o in hops]
+        return [g.propagate(h, transpose=transpose, add=a, out=o, internal=True) for h, a, o in hops]
     rp = g.t[0] if transpose else g.rowptr
     return spmm_chain(rp, g._edges_t if transpose else g.edges, g.self_w if g.mode == "gcn" else None, hops,
                       self_loop=g.mode == "gcn", tile_ptr=g.tile_ptr, n_tiles=g.n_tiles)
@@ -238,19 +316,20 @@ _CSR_CACHE = {}
 _CSR_CACHE_MAX = 16
 
 
-def graph_csr(edge_index, num_nodes, mode="tag", ptr_host=None):
+def graph_csr(edge_index, num_nodes, mode="tag", ptr_host=None, reorder=True):
     """Structure cache: ``conv(x, edge_index)`` (models/model.py:71,77) passes the same
     ``edge_index`` tensor to every layer and hop, so the CSR pair is built once per batch.
     Keyed on storage identity + version; the entry pins the tensor so the address cannot be
     recycled while cached."""
     if isinstance(edge_index, GraphCSR):
         return edge_index
+    reorder = bool(reorder) and _eligible_order(edge_index, int(num_nodes), mode, ptr_host) is not None
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), mode,
-           edge_index.device.index)
+           edge_index.device.index, reorder)
     hit = _CSR_CACHE.get(key)
     if hit is not None:
         return hit
-    g = GraphCSR(edge_index, num_nodes, mode, ptr_host)
+    g = GraphCSR(edge_index, num_nodes, mode, ptr_host, reorder=reorder)
     if len(_CSR_CACHE) >= _CSR_CACHE_MAX:
         _CSR_CACHE.pop(next(iter(_CSR_CACHE)))
     _CSR_CACHE[key] = g
@@ -552,7 +631,9 @@ def knn_table(pos, k, batch=None, ptr=None, loop=False):
     if _use_grid(N, batch, ptr, W):
         nb = _abi.lib().dc_knn_grid_workspace_bytes(N)
         ws = _workspace(nb, pos.device)
-        _abi.call("dc_knn_grid", _ptr(pos), N, k, int(bool(loop)), _ptr(tab), _ptr(ws), nb, _stream())
+        order = torch.empty(N, dtype=_i32, device=pos.device) if REORDER and N >= REORDER_MIN_NODES else None
+        _abi.call("dc_knn_grid", _ptr(pos), N, k, int(bool(loop)), _ptr(tab), _ptr(order), _ptr(ws), nb, _stream())
+        tab._cell_order = order     # the search's own counting sort doubles as the spatial node order (ops.REORDER)
         return tab
     p = _ptr_tensor(N, batch, ptr, pos.device)
     _abi.call("dc_knn", _ptr(pos), _ptr(p), p.numel() - 1, N, k, int(bool(loop)), _ptr(tab), _stream())
@@ -569,8 +650,10 @@ def radius_table(pos, r, batch=None, ptr=None, loop=False, max_num_neighbors=32)
     if _use_grid(N, batch, ptr, W):
         nb = _abi.lib().dc_knn_grid_workspace_bytes(N)
         ws = _workspace(nb, pos.device)
-        _abi.call("dc_radius_grid", _ptr(pos), N, float(r), max_num_neighbors, int(bool(loop)), _ptr(tab), _ptr(cnt), _ptr(ws), nb,
-                  _stream())
+        order = torch.empty(N, dtype=_i32, device=pos.device) if REORDER and N >= REORDER_MIN_NODES else None
+        _abi.call("dc_radius_grid", _ptr(pos), N, float(r), max_num_neighbors, int(bool(loop)), _ptr(tab), _ptr(cnt), _ptr(order),
+                  _ptr(ws), nb, _stream())
+        tab._cell_order = order
         return tab, cnt
     p = _ptr_tensor(N, batch, ptr, pos.device)
     _abi.call("dc_radius", _ptr(pos), _ptr(p), p.numel() - 1, N, float(r), max_num_neighbors, int(bool(loop)), _ptr(tab),

@@ -88,14 +88,14 @@ def tag_conv(x: Tensor, edge_index: Tensor, weights: List[Tensor], bias: Optiona
     N, Fi = x.shape
     K = len(weights) - 1
     buf = torch.empty((N, max(K, 1) * Fi), dtype=x.dtype, device=x.device)
-    hs = [x]
+    hs = [g.to_internal(x)]   # a relabelled large graph (ops.REORDER) runs the whole layer in its own node order
     for k in range(K):
         hs.append(buf[:, k * Fi:(k + 1) * Fi])
     if K:
-        ops.propagate_chain(g, [(hs[k], None, hs[k + 1]) for k in range(K)])   # h_{k+1} = A_hat h_k (one launch, K1 v9)
+        ops.propagate_chain(g, [(hs[k], None, hs[k + 1]) for k in range(K)], internal=True)   # h_{k+1} = A_hat h_k (one launch, K1 v9)
     out = ops.gemm([(h, w) for h, w in zip(hs, weights)], N, weights[0].shape[0], False, True, bias=bias, relu=relu,
                    precision=precision)
-    return out, buf
+    return g.from_internal(out), buf
 
 
 @tag_conv.register_fake
@@ -113,10 +113,11 @@ def tag_conv_backward(dout: Tensor, out: Tensor, x: Tensor, hops: Tensor, edge_i
     dout = dout.contiguous()
     if relu:
         dout = ops.relu_bwd(out, dout)
+    dout = g.to_internal(dout)      # the saved hops are in the structure's node order
     N, Fo = dout.shape
     Fi = x.shape[1]
     K = len(weights) - 1
-    hs = [x.contiguous()] + [hops[:, k * Fi:(k + 1) * Fi] for k in range(K)]
+    hs = [g.to_internal(x.contiguous())] + [hops[:, k * Fi:(k + 1) * Fi] for k in range(K)]
     if need_dw:
         dws = torch.empty((K + 1, Fo, Fi), dtype=dout.dtype, device=dout.device)
         for k, h in enumerate(hs):
@@ -129,13 +130,13 @@ def tag_conv_backward(dout: Tensor, out: Tensor, x: Tensor, hops: Tensor, edge_i
         if ops.K1_CHAIN >= 2 and K > 0:
             # all dH_k first, then the transposed hops as one chain, accumulating in place: dH_{k-1} += A_hat^T g_k
             dhs = [ops.gemm([(dout, weights[k])], N, Fi, False, False, precision=precision) for k in range(K)] + [gk]
-            ops.propagate_chain(g, [(dhs[k + 1], dhs[k], dhs[k]) for k in range(K - 1, -1, -1)], transpose=True)
+            ops.propagate_chain(g, [(dhs[k + 1], dhs[k], dhs[k]) for k in range(K - 1, -1, -1)], transpose=True, internal=True)
             gk = dhs[0]
         else:
             for k in range(K - 1, -1, -1):
                 dhk = ops.gemm([(dout, weights[k])], N, Fi, False, False, precision=precision)
-                gk = g.propagate(gk, transpose=True, add=dhk)
-        dx = gk
+                gk = g.propagate(gk, transpose=True, add=dhk, internal=True)
+        dx = g.from_internal(gk)
     else:
         dx = dout.new_empty(0)
     return dx, db, dws

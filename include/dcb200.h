@@ -264,10 +264,18 @@ DC_API int dc_radius(const float* pos, const int64_t* ptr, int64_t num_graphs, i
  * are bit-identical to dc_knn / dc_radius (same distances, keys and tie rule; radius keeps the lowest indices).  All
  * grid parameters are computed on the device (no host sync).  Worth it from a few ten thousand points up. */
 DC_API size_t dc_knn_grid_workspace_bytes(int64_t num_points);
-DC_API int dc_knn_grid(const float* pos, int64_t num_points, int32_t k, int loop, int32_t* nbr_out, void* workspace,
-                size_t workspace_bytes, dc_stream_t stream);
+/* order_out (int32 [N], may be NULL): the points in grid-cell order, as dc_cell_order returns it. */
+DC_API int dc_knn_grid(const float* pos, int64_t num_points, int32_t k, int loop, int32_t* nbr_out, int32_t* order_out,
+                void* workspace, size_t workspace_bytes, dc_stream_t stream);
 DC_API int dc_radius_grid(const float* pos, int64_t num_points, float r, int32_t max_nbr, int loop, int32_t* nbr_out,
-                   int32_t* count_out, void* workspace, size_t workspace_bytes, dc_stream_t stream);
+                   int32_t* count_out, int32_t* order_out, void* workspace, size_t workspace_bytes, dc_stream_t stream);
+/* order[i] = index of the i-th point in grid-cell order (the counting sort of K4g): a spatially coherent relabelling
+ * of a large point cloud.  A permutation of 0..N-1; the order inside a cell is unspecified.  Workspace as dc_knn_grid. */
+DC_API int dc_cell_order(const float* pos, int64_t num_points, int32_t* order, void* workspace, size_t workspace_bytes,
+                  dc_stream_t stream);
+/* out[i, :] = in[perm[i], :] (fp32 rows; in != out).  Used to run the hops of a large single graph in cell order. */
+DC_API int dc_permute_rows(const float* in, int64_t ldin, const int32_t* perm, float* out, int64_t ldout, int64_t num_rows,
+                    int32_t F, dc_stream_t stream);
 /* Compacts a padded neighbour table into edge_index int64 [2, E_cap] (row 0 = neighbour,
  * row 1 = query), queries ascending; *num_edges_out (device int64) receives E. */
 DC_API size_t dc_nbr_to_edge_index_workspace_bytes(int64_t num_points);

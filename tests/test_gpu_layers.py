@@ -223,3 +223,52 @@ def test_graphnet_with_mpnn_backbone(dc):
     cu = lambda b: dc.Batch.from_data_list([dc.Data(x=d.x, edge_index=d.edge_index, pos=d.pos) for d in (b[0], b[1])]).to("cuda")
     # 21 / 25-d inputs are not multiples of 4 -> fine for the GEMMs; edge kernel runs at the hidden width
     assert_close(ours(cu(rest), cu(rigid)).pos, ref(rest, rigid).pos, tol=2e-5, what="GraphNet[MPNN]")
+
+
+def test_large_single_graph_runs_in_cell_order_with_identical_results():
+    """ops.REORDER: a single large cloud's kNN graph carries the grid-cell order of its points; TAGConv / GCNConv then
+    run their hops on relabelled nodes.  Hops are bit-identical (same per-receiver edge order); layer outputs and input
+    gradients are bit-identical too (row-wise GEMMs); weight gradients (a sum over all nodes) agree to 1e-5."""
+    import deformcontact_b200 as dc
+    from deformcontact_b200 import ops
+    gen = torch.Generator().manual_seed(8)
+    N, F = 40000, 64
+    pos = torch.rand(N, 3, generator=gen).cuda()
+    x = torch.randn(N, F, generator=gen).cuda()
+    gout = torch.randn(N, F, generator=gen).cuda()
+    ei = dc.knn_graph(pos, 8)
+    order = ops.cell_order(pos)
+    assert torch.equal(order.long().sort().values, torch.arange(N, device="cuda"))      # a permutation
+    res = {}
+    try:
+        for flag in (True, False):
+            ops.REORDER = flag
+            ops.clear_csr_cache()
+            g = ops.graph_csr(ei, N, "tag", None)
+            assert (g.order is not None) == flag
+            add = torch.randn(N, F, generator=torch.Generator().manual_seed(1)).cuda()
+            hop = g.propagate(x)
+            hop_t = g.propagate(x, transpose=True, add=add)
+            torch.manual_seed(0)
+            layer = dc.TAGConv(F, F).cuda()
+            xx = x.clone().requires_grad_(True)
+            out = layer(xx, ei, relu=True)
+            out.backward(gout)
+            torch.manual_seed(0)
+            gcn = dc.GCNConv(F, F).cuda()
+            res[flag] = dict(hop=hop, hop_t=hop_t, out=out.detach(), dx=xx.grad.clone(), dw=[l.weight.grad.clone() for l in layer.lins],
+                             db=layer.bias.grad.clone(), gcn=gcn(x, ei).detach())
+            # the fused losses read the structure with positions in their original order: unaffected by the relabelling
+            pred = dc.Data(x=None, edge_index=ei, pos=pos + 0.01)
+            tgt = dc.Data(x=None, edge_index=ei, pos=pos)
+            res[flag]["loss"] = [float(v) for v in dc.fused_losses(pred, tgt)]
+    finally:
+        ops.REORDER = True
+        ops.clear_csr_cache()
+    a, b = res[True], res[False]
+    for k in ("hop", "hop_t", "out", "dx", "gcn"):
+        assert torch.equal(a[k], b[k]), k
+    for wa, wb in zip(a["dw"], b["dw"]):
+        assert_close(wa, wb, what="dW reordered vs not")
+    assert_close(a["db"], b["db"], what="db reordered vs not")
+    assert a["loss"] == b["loss"]
