@@ -457,6 +457,23 @@ def _ev_time(fn, reps, warmup=3):
     return e0.elapsed_time(e1) / reps
 
 
+def _ev_median(fn, reps, warmup=2):
+    """Median of per-call CUDA-event times: robust against one-off host stalls (the clock sampler's nvidia-smi calls can hold
+    the driver for tens of ms, which would dominate the mean of a few sub-millisecond calls)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
 def run_infer_c2(args):
     """C2: everyday.json model inference, batch 64 synthetic meshes x ~5k nodes, 1 GPU."""
     import deformcontact_b200 as dc
@@ -508,13 +525,13 @@ def run_mesh_c4(args):
     layers = torch.nn.ModuleList([dc.TAGConv(21 if i == 0 else 256, 256) for i in range(L)]).to(dev)
     sampler = ClockSampler(0)
     sampler.start()
-    knn_ms = _ev_time(lambda: dc.knn_graph(pos, k), max(2, args.steps // 2), 1)     # auto: uniform grid (K4g) for one large cloud
+    knn_ms = _ev_median(lambda: dc.knn_graph(pos, k), 15)     # auto: uniform grid (K4g) for one large cloud; median of 15 calls
     ops.KNN_MODE = "brute"
-    knn_brute_ms = _ev_time(lambda: dc.knn_graph(pos, k), 2, 1)                      # tiled brute force (K4), same result
+    knn_brute_ms = _ev_median(lambda: dc.knn_graph(pos, k), 3, 1)                    # tiled brute force (K4), same result
     ops.KNN_MODE = "auto"
     ei = dc.knn_graph(pos, k)
     radius = (3.0 * k / (4.0 * 3.141592653589793 * N)) ** (1.0 / 3.0)   # ~k neighbours per point at this density
-    radius_ms = _ev_time(lambda: dc.radius_graph(pos, radius), max(2, args.steps // 2), 1)
+    radius_ms = _ev_median(lambda: dc.radius_graph(pos, radius), 15)
     radius_edges = dc.radius_graph(pos, radius).shape[1]
     x0 = dc.to_log_freq(pos)
 

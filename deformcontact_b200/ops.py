@@ -6,6 +6,7 @@ where a data-dependent output size must be read back: ``knn_graph`` / ``radius_g
 PyTorch is plumbing here: device memory and streams.  No eager fallback exists.
 """
 import ctypes as C
+import weakref
 
 import torch
 
@@ -147,15 +148,19 @@ def _hint_key(edge_index):
 
 
 def register_order_hint(edge_index, order):
-    """``order`` int32 [N]: a spatially coherent permutation of the nodes (new position -> node id) for this edge_index."""
-    if len(_ORDER_HINTS) >= 8:
-        _ORDER_HINTS.pop(next(iter(_ORDER_HINTS)))
-    _ORDER_HINTS[_hint_key(edge_index)] = (edge_index, order)   # the entry pins the tensor so its address cannot be recycled
+    """``order`` int32 [N]: a spatially coherent permutation of the nodes (new position -> node id) for this edge_index.
+    The table holds only a weak reference: the hint lives exactly as long as the tensor (while it is alive its storage
+    address cannot be recycled, so the key is unambiguous; nothing is pinned)."""
+    for k in [k for k, (ref, _) in _ORDER_HINTS.items() if ref() is None]:
+        del _ORDER_HINTS[k]
+    _ORDER_HINTS[_hint_key(edge_index)] = (weakref.ref(edge_index), order)
 
 
 def _order_hint(edge_index, num_nodes):
     hit = _ORDER_HINTS.get(_hint_key(edge_index))
-    return hit[1] if hit is not None and hit[1].numel() == num_nodes else None
+    if hit is None or hit[0]() is None or hit[1].numel() != num_nodes:
+        return None
+    return hit[1]
 
 
 def _eligible_order(edge_index, num_nodes, mode, ptr_host):

@@ -18,3 +18,4 @@ python scripts/step_profile.py > gpurun_out/step_profile.txt 2>&1; tail -30 gpur
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 90000 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_under_ncu.log 2>&1
 wc -l gpurun_out/launches.csv
+for t in memcheck racecheck synccheck; do timeout 400 compute-sanitizer --tool $t python scripts/sanitize.py > gpurun_out/san_$t.log 2>&1; echo "$t rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize run ok" gpurun_out/san_$t.log | tail -2; done

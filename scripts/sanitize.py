@@ -17,6 +17,13 @@ ops.KNN_MODE = "grid"   # K4g: uniform-grid search (bounding box, counting sort,
 dc.knn_graph(pos, 16); dc.knn_graph(pos, 70, loop=True); dc.radius_graph(pos, 0.2); dc.radius_graph(pos, 0.3, max_num_neighbors=5)
 dc.knn_graph(torch.full((50, 3), 0.5, device="cuda"), 4)
 ops.KNN_MODE = "auto"
+# relabelled large single graph (ops.REORDER): cell order from the grid search, permuted hops, TAGConv fwd + bwd
+big = torch.rand(ops.REORDER_MIN_NODES + 100, 3, device="cuda")
+ei_big = dc.knn_graph(big, 6)
+xb = torch.randn(big.shape[0], 32, device="cuda", requires_grad=True)
+dc.TAGConv(32, 32).cuda()(xb, ei_big, relu=True).sum().backward()
+dc.GCNConv(32, 32).cuda()(xb.detach(), ei_big)
+ops.cell_order(big)
 # N3 batch assembly: every entry point, ragged inputs, int32 and int64 local indices
 parts = [rest[i] for i in range(2)]
 cpu = lambda t: t.cpu()
