@@ -152,3 +152,68 @@ def test_flat_grad_allreduce_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_order_hints_are_weak_and_scoped():
+    """ops.REORDER host logic: a hint lives as long as its edge_index tensor, is never pinned, and only one large
+    TAG / GCN graph qualifies for relabelling."""
+    import gc
+    from deformcontact_b200 import ops
+    n = ops.REORDER_MIN_NODES
+    ei = torch.zeros((2, 7), dtype=torch.long)
+    order = torch.arange(n, dtype=torch.int32)
+    ops.register_order_hint(ei, order)
+    assert ops._order_hint(ei, n) is order
+    assert ops._order_hint(ei, n + 1) is None                              # node count must match
+    assert ops._order_hint(torch.zeros((2, 7), dtype=torch.long), n) is None   # another tensor, another address
+    assert ops._eligible_order(ei, n, "tag", None) is order
+    assert ops._eligible_order(ei, n, "gcn", [0, n]) is order             # a single graph given as ptr
+    assert ops._eligible_order(ei, n, "gat", None) is None                # GAT kernels read the CSR directly
+    assert ops._eligible_order(ei, n, "tag", [0, 5, n]) is None           # block-diagonal batch: tiled by graph instead
+    assert ops._eligible_order(ei, n - 1, "tag", None) is None            # small graph
+    old, ops.REORDER = ops.REORDER, False
+    try:
+        assert ops._eligible_order(ei, n, "tag", None) is None
+    finally:
+        ops.REORDER = old
+    key = ops._hint_key(ei)
+    del ei
+    gc.collect()
+    assert ops._ORDER_HINTS[key][0]() is None                              # the table did not keep the tensor alive
+    ops.register_order_hint(torch.zeros((2, 3), dtype=torch.long), order)  # registering prunes dead entries
+    assert key not in ops._ORDER_HINTS
+
+
+def test_tiles_are_closed_only_for_whole_graphs():
+    """The hop chain (K1 v9) needs every tile to be closed under the edges: make_tiles merges small graphs and never
+    splits one unless it exceeds the tile budget; the closure test is 'every tile boundary is a graph boundary'."""
+    from deformcontact_b200 import ops
+    ptr = [0, 762, 1524, 2286, 3048, 5048, 7048]                          # colliders (merged) + soft graphs
+    tiles = ops.make_tiles(ptr, ptr[-1])
+    assert tiles[0] == 0 and tiles[-1] == ptr[-1] and set(tiles) <= set(ptr)
+    assert max(b - a for a, b in zip(tiles[:-1], tiles[1:])) <= ops.TILE_NODES + ops.TILE_NODES // 4
+    big = [0, 3 * ops.TILE_NODES]                                          # one large graph is split -> not closed
+    assert not set(ops.make_tiles(big, big[-1])) <= set(big)
+    assert ops.make_tiles(None, 100) is None
+
+
+def test_packer_layout_is_aligned_and_roundtrips():
+    """assemble._Packer: typed arrays at 256-byte aligned offsets of one byte buffer; the same plan carves the device copy."""
+    from deformcontact_b200 import assemble
+    pk = assemble._Packer()
+    pk.add("a", torch.int64, (3,))
+    pk.add("b", torch.float32, (5, 3))
+    pk.add("c", torch.int32, (2, 0))
+    pk.add("d", torch.float64, (2, 3))
+    assert all(off % 256 == 0 for _, _, _, off, _ in pk.fields) and pk.total % 256 == 0
+    buf = torch.zeros(pk.total, dtype=torch.uint8)
+    v = pk.views(buf)
+    v["a"].copy_(torch.tensor([1, 2, 3]))
+    v["b"].copy_(torch.arange(15.0).reshape(5, 3))
+    v["d"].fill_(0.5)
+    w = pk.views(buf.clone())
+    assert w["a"].tolist() == [1, 2, 3] and torch.equal(w["b"], torch.arange(15.0).reshape(5, 3))
+    assert w["c"].shape == (2, 0) and w["d"].dtype == torch.float64 and float(w["d"].sum()) == 3.0
+    assert assemble._cumsum0([2, 0, 5]) == [0, 2, 2, 7]
+    with pytest.raises(Exception):
+        assemble.batch_from_data_list([], device="cuda")
