@@ -58,9 +58,13 @@ class Batch(Data):
     def from_data_list(cls, data_list, device=None):
         """PyG layout (data/batch.py).  With ``device`` a CUDA device and CPU inputs, the batch is assembled on the
         GPU from one packed copy (``assemble.batch_from_data_list`` = ``from_data_list(...).to(device)``)."""
-        if device is not None and torch.device(device).type == "cuda":
+        data_list = list(data_list)
+        on_host = all(t is None or not t.is_cuda for d in data_list for t in (d.x, d.pos, d.edge_index))
+        if device is not None and torch.device(device).type == "cuda" and on_host and data_list:
             from .assemble import batch_from_data_list
             return batch_from_data_list(data_list, device=device)
+        if device is not None:                       # graphs already on a device (or a CPU target): concatenate, then move
+            return cls.from_data_list(data_list).to(device)
         sizes = [d.num_nodes for d in data_list]
         esizes = [d.num_edges for d in data_list]
         ref = next((t for d in data_list for t in (d.x, d.pos, d.edge_index) if t is not None), None)
