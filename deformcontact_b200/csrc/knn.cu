@@ -38,7 +38,8 @@ __device__ __forceinline__ int find_graph(const int64_t* __restrict__ ptr, int64
 template <int SLOTS, int QW>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, int64_t B, int64_t N, int kk, int loop, int W,
-           int32_t* __restrict__ out) {
+           int32_t* __restrict__ out, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;   // device-side dispatch (knn_grid.cu): the grid search took this cloud
   __shared__ float sx[TILE], sy[TILE], sz[TILE];
   constexpr int QB = KNN_WARPS * QW;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -137,7 +138,8 @@ knn_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, int64
 
 __global__ void __launch_bounds__(KNN_THREADS)
 radius_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, int64_t B, int64_t N, float r2, int cap,
-              int loop, int W, int32_t* __restrict__ out, int32_t* __restrict__ count_out) {
+              int loop, int W, int32_t* __restrict__ out, int32_t* __restrict__ count_out, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;   // device-side dispatch (knn_grid.cu): the grid search took this cloud
   __shared__ float sx[TILE], sy[TILE], sz[TILE];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t qb0 = (int64_t)blockIdx.x * RQB;
@@ -274,6 +276,27 @@ __global__ void nbr_emit_kernel(const int32_t* __restrict__ nbr, int64_t N, int 
 }
 }  // namespace
 
+// The two brute-force launches, shared with knn_grid.cu (its fallback for clouds a uniform grid cannot split).  `skip`
+// (device int, may be NULL): the kernels return at once when *skip != 0.
+namespace dcb {
+int launch_knn_brute(const float* pos, const int64_t* ptr, int64_t B, int64_t N, int kk, int loop, int32_t* nbr_out,
+                     const int* skip, cudaStream_t st) {
+  // 8 queries per warp while the candidate set is one key per lane; fewer for wide sets (register budget)
+  if (kk <= 32) knn_kernel<1, 8><<<(unsigned)cdiv(N, KNN_WARPS * 8), KNN_THREADS, 0, st>>>(pos, ptr, B, N, kk, loop, kk, nbr_out, skip);
+  else if (kk <= 64) knn_kernel<2, 4><<<(unsigned)cdiv(N, KNN_WARPS * 4), KNN_THREADS, 0, st>>>(pos, ptr, B, N, kk, loop, kk, nbr_out, skip);
+  else knn_kernel<4, 4><<<(unsigned)cdiv(N, KNN_WARPS * 4), KNN_THREADS, 0, st>>>(pos, ptr, B, N, kk, loop, kk, nbr_out, skip);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+int launch_radius_brute(const float* pos, const int64_t* ptr, int64_t B, int64_t N, float r2, int cap, int loop,
+                        int32_t* nbr_out, int32_t* count_out, const int* skip, cudaStream_t st) {
+  radius_kernel<<<(unsigned)cdiv(N, RQB), KNN_THREADS, 0, st>>>(pos, ptr, B, N, r2, cap, loop, cap, nbr_out, count_out, skip);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+}  // namespace dcb
+
 extern "C" int dc_knn(const float* pos, const int64_t* ptr, int64_t B, int64_t N, int32_t k, int loop, int32_t* nbr_out,
                       dc_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
@@ -282,12 +305,7 @@ extern "C" int dc_knn(const float* pos, const int64_t* ptr, int64_t B, int64_t N
   DC_REQUIRE(pos && ptr && nbr_out, DC_EINVAL, "knn: null pointer");
   const int kk = k + (loop ? 0 : 1);
   DC_REQUIRE(kk <= 128, DC_ENOSUP, "knn: k=%d exceeds the supported maximum (127, or 128 with loop)", k);
-  // 8 queries per warp while the candidate set is one key per lane; fewer for wide sets (register budget)
-  if (kk <= 32) knn_kernel<1, 8><<<(unsigned)cdiv(N, KNN_WARPS * 8), KNN_THREADS, 0, st>>>(pos, ptr, B, N, kk, loop, kk, nbr_out);
-  else if (kk <= 64) knn_kernel<2, 4><<<(unsigned)cdiv(N, KNN_WARPS * 4), KNN_THREADS, 0, st>>>(pos, ptr, B, N, kk, loop, kk, nbr_out);
-  else knn_kernel<4, 4><<<(unsigned)cdiv(N, KNN_WARPS * 4), KNN_THREADS, 0, st>>>(pos, ptr, B, N, kk, loop, kk, nbr_out);
-  DC_LAUNCH_CHECK();
-  return DC_OK;
+  return dcb::launch_knn_brute(pos, ptr, B, N, kk, loop, nbr_out, nullptr, st);
 }
 
 extern "C" int dc_radius(const float* pos, const int64_t* ptr, int64_t B, int64_t N, float r, int32_t max_nbr, int loop,
@@ -298,9 +316,7 @@ extern "C" int dc_radius(const float* pos, const int64_t* ptr, int64_t B, int64_
   DC_REQUIRE(pos && ptr && nbr_out, DC_EINVAL, "radius: null pointer");
   const int cap = max_nbr + (loop ? 0 : 1);
   const float r2 = r * r;  // fp32 product, as torch_cluster
-  radius_kernel<<<(unsigned)cdiv(N, RQB), KNN_THREADS, 0, st>>>(pos, ptr, B, N, r2, cap, loop, cap, nbr_out, count_out);
-  DC_LAUNCH_CHECK();
-  return DC_OK;
+  return dcb::launch_radius_brute(pos, ptr, B, N, r2, cap, loop, nbr_out, count_out, nullptr, st);
 }
 
 extern "C" size_t dc_nbr_to_edge_index_workspace_bytes(int64_t N) {

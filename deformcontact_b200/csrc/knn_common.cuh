@@ -3,6 +3,14 @@
 #pragma once
 #include "common.cuh"
 
+namespace dcb {
+// brute-force launches of knn.cu (also the fallback of knn_grid.cu); `skip`: device flag, kernels return when *skip != 0
+int launch_knn_brute(const float* pos, const int64_t* ptr, int64_t B, int64_t N, int kk, int loop, int32_t* nbr_out,
+                     const int* skip, cudaStream_t st);
+int launch_radius_brute(const float* pos, const int64_t* ptr, int64_t B, int64_t N, float r2, int cap, int loop,
+                        int32_t* nbr_out, int32_t* count_out, const int* skip, cudaStream_t st);
+}  // namespace dcb
+
 namespace {
 using namespace dcb;
 

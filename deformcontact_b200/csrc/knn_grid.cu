@@ -12,6 +12,7 @@
 // so unvisited points can never belong to the answer; ties are resolved by the exact key compare as in knn.cu.
 // Radius search keeps the `cap` SMALLEST INDICES among the hits (the brute-force kernel's "first by index" rule) with
 // the same top-k machinery on keys = index.
+#include <cstddef>
 #include "common.cuh"
 #include "scan.cuh"
 #include "knn_common.cuh"
@@ -24,7 +25,13 @@ struct GridParams {
   float inv_h, h, margin;   // margin: absolute slack of the stop test (>> rounding of the cell assignment)
   int dim[3];
   int cells;
+  int use_grid;            // device-side dispatch: 1 = the grid search runs, 0 = the brute-force kernels take the cloud
+  int pad_;
+  int64_t ptr[2];          // {0, N}: the one-cloud `ptr` the brute-force kernels expect
+  unsigned long long cost; // sum over cells of count^2 (x27 = candidate visits of the first ring)
 };
+static_assert(offsetof(GridParams, use_grid) == 40 && offsetof(GridParams, ptr) == 48 && sizeof(GridParams) == 72,
+              "GridParams layout is read by ops.grid_took_it");
 
 constexpr int BB_THREADS = 256;
 constexpr int BB_BLOCKS = 296;   // 2 x 148 partial bounding boxes
@@ -63,7 +70,7 @@ bbox_partial_kernel(const float* __restrict__ pos, int64_t N, float* __restrict_
 
 // one thread: final bounding box, cell size for `target_cells` cells over the longest extent, grid dimensions
 __global__ void grid_params_kernel(const float* __restrict__ partial, int nblocks, int64_t target_cells, int64_t max_cells,
-                                   GridParams* __restrict__ gp) {
+                                   int64_t N, GridParams* __restrict__ gp) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (int b = 0; b < nblocks; ++b)
@@ -88,7 +95,31 @@ __global__ void grid_params_kernel(const float* __restrict__ partial, int nblock
     for (int d = 0; d < 3; ++d) amax = fmaxf(amax, fmaxf(fabsf(mn[d]), fabsf(mx[d])));
     g.margin = 1.0e-5f * (emax + amax);   // ~100 ulp of the largest coordinate / extent
   }
+  g.use_grid = 1; g.pad_ = 0; g.ptr[0] = 0; g.ptr[1] = N; g.cost = 0ull;
   *gp = g;
+}
+
+// A uniform grid only pays while no cell holds a large share of the cloud (one far outlier, two distant clusters, ... put
+// almost everything into a few cells and every query would scan them 32 candidates at a time).  cost = sum count^2 estimates
+// the candidate visits (x27 for the first ring); the tiled brute-force kernel needs N^2 pair tests at a ~5x lower price
+// each.  The decision is taken on the device (no host sync): both searches are launched, one returns immediately.
+__global__ void __launch_bounds__(256)
+grid_cost_kernel(const uint32_t* __restrict__ start, GridParams* __restrict__ gp) {
+  const int cells = gp->cells;
+  unsigned long long c = 0ull;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += gridDim.x * blockDim.x) {
+    const unsigned long long n = start[i + 1] - start[i];
+    c += n * n;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&gp->cost, c);
+}
+
+__global__ void grid_decide_kernel(GridParams* __restrict__ gp, int64_t N) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double visits = 27.0 * 5.0 * (double)gp->cost;
+  gp->use_grid = visits <= (double)N * (double)N ? 1 : 0;
 }
 
 __device__ __forceinline__ int cell_coord(float p, float lo, float inv_h, int dim) {
@@ -131,6 +162,7 @@ grid_search_kernel(const float4* __restrict__ sorted, const uint32_t* __restrict
   const int64_t w = (int64_t)blockIdx.x * (GRID_THREADS / 32) + (threadIdx.x >> 5);
   if (w >= N) return;   // warp-uniform
   const GridParams g = *gp;
+  if (!g.use_grid) return;   // the brute-force kernels take this cloud (see grid_decide_kernel)
   const float4 qp = sorted[w];
   const int64_t q = (int64_t)__float_as_int(qp.w);
   const int cx = cell_coord(qp.x, g.lo[0], g.inv_h, g.dim[0]);
@@ -256,13 +288,15 @@ int build_grid(const float* pos, int64_t N, const GridWs& g, cudaStream_t st) {
   DC_CUDA(cudaMemsetAsync(g.count, 0, (mc + 1) * sizeof(uint32_t), st));
   DC_CUDA(cudaMemsetAsync(g.cursor, 0, (mc + 1) * sizeof(uint32_t), st));
   bbox_partial_kernel<<<BB_BLOCKS, BB_THREADS, 0, st>>>(pos, N, g.partial);
-  grid_params_kernel<<<1, 32, 0, st>>>(g.partial, BB_BLOCKS, grid_target_cells(N), mc, g.gp);
+  grid_params_kernel<<<1, 32, 0, st>>>(g.partial, BB_BLOCKS, grid_target_cells(N), mc, N, g.gp);
   const unsigned nb = (unsigned)std::min<int64_t>(cdiv(N, 256), (int64_t)kSMs * 16);
   cell_count_kernel<<<nb, 256, 0, st>>>(pos, N, g.gp, g.cell_of, g.count);
   DC_LAUNCHED(3);
   if (int rc = exclusive_scan_u32(g.count, mc + 1, g.bsum, st)) return rc;   // unused cells keep start = N
   cell_scatter_kernel<<<nb, 256, 0, st>>>(pos, N, g.cell_of, g.count, g.cursor, g.sorted);
-  DC_LAUNCH_CHECK();
+  grid_cost_kernel<<<(unsigned)std::min<int64_t>(cdiv(mc, 256), 64), 256, 0, st>>>(g.count, g.gp);
+  grid_decide_kernel<<<1, 32, 0, st>>>(g.gp, N);
+  DC_LAUNCHED(3);
   return DC_OK;
 }
 }  // namespace
@@ -294,6 +328,7 @@ extern "C" int dc_knn_grid(const float* pos, int64_t N, int32_t k, int loop, int
   else if (kk <= 64) grid_search_kernel<2, 0><<<grid, GRID_THREADS, 0, st>>>(g.sorted, g.count, g.gp, N, kk, loop, kk, 0.f, nbr_out, nullptr);
   else grid_search_kernel<4, 0><<<grid, GRID_THREADS, 0, st>>>(g.sorted, g.count, g.gp, N, kk, loop, kk, 0.f, nbr_out, nullptr);
   DC_LAUNCH_CHECK();
+  if (int rc = launch_knn_brute(pos, g.gp->ptr, 1, N, kk, loop, nbr_out, &g.gp->use_grid, st)) return rc;   // runs iff use_grid == 0
   if (order_out) {
     extract_order_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(g.sorted, N, order_out);
     DC_LAUNCH_CHECK();
@@ -319,6 +354,7 @@ extern "C" int dc_radius_grid(const float* pos, int64_t N, float r, int32_t max_
   else if (cap <= 64) grid_search_kernel<2, 1><<<grid, GRID_THREADS, 0, st>>>(g.sorted, g.count, g.gp, N, cap, loop, cap, r2, nbr_out, count_out);
   else grid_search_kernel<4, 1><<<grid, GRID_THREADS, 0, st>>>(g.sorted, g.count, g.gp, N, cap, loop, cap, r2, nbr_out, count_out);
   DC_LAUNCH_CHECK();
+  if (int rc = launch_radius_brute(pos, g.gp->ptr, 1, N, r2, cap, loop, nbr_out, count_out, &g.gp->use_grid, st)) return rc;
   if (order_out) {
     extract_order_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(g.sorted, N, order_out);
     DC_LAUNCH_CHECK();

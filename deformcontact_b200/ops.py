@@ -639,6 +639,7 @@ def knn_table(pos, k, batch=None, ptr=None, loop=False):
         order = torch.empty(N, dtype=_i32, device=pos.device) if REORDER and N >= REORDER_MIN_NODES else None
         _abi.call("dc_knn_grid", _ptr(pos), N, k, int(bool(loop)), _ptr(tab), _ptr(order), _ptr(ws), nb, _stream())
         tab._cell_order = order     # the search's own counting sort doubles as the spatial node order (ops.REORDER)
+        tab._grid_ws = ws           # tests read the device-side grid / brute-force decision out of it (grid_took_it)
         return tab
     p = _ptr_tensor(N, batch, ptr, pos.device)
     _abi.call("dc_knn", _ptr(pos), _ptr(p), p.numel() - 1, N, k, int(bool(loop)), _ptr(tab), _stream())
@@ -664,6 +665,15 @@ def radius_table(pos, r, batch=None, ptr=None, loop=False, max_num_neighbors=32)
     _abi.call("dc_radius", _ptr(pos), _ptr(p), p.numel() - 1, N, float(r), max_num_neighbors, int(bool(loop)), _ptr(tab),
               _ptr(cnt), _stream())
     return tab, cnt
+
+
+def grid_took_it(tab):
+    """True if the uniform-grid kernel produced this table, False if the library's device-side dispatch handed the cloud to
+    the brute-force kernel (a grid cannot split it: outliers, few dense clusters).  Reads one int back (host sync)."""
+    ws = getattr(tab, "_grid_ws", None)
+    if ws is None:
+        return False
+    return bool(ws[40:44].view(torch.int32).item())   # GridParams::use_grid at byte 40 (static_assert in csrc/knn_grid.cu)
 
 
 def table_to_edge_index(tab):

@@ -492,3 +492,22 @@ def test_grid_search_large_cloud_vs_oracle_and_auto_dispatch(dc):
     assert torch.equal(tab, want)
     # batched clouds never take the grid path
     assert not ops._use_grid(40000, torch.zeros(40000, dtype=torch.long), None, 17)
+
+
+def test_grid_search_hands_unsplittable_clouds_to_brute_force(dc):
+    """Device-side dispatch of K4g: one far outlier puts the whole cloud into one cell -> the brute-force kernel runs (no
+    performance cliff), a uniform cloud stays on the grid; the output is the same either way."""
+    from deformcontact_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    uni = torch.rand(20000, 3, generator=g)
+    outlier = torch.cat([uni, torch.tensor([[1.0e4, 1.0e4, 1.0e4]])])
+    try:
+        for pos, want_grid in ((uni.cuda(), True), (outlier.cuda(), False)):
+            ops.KNN_MODE = "brute"
+            ref = ops.knn_table(pos, 16)
+            ops.KNN_MODE = "grid"
+            out = ops.knn_table(pos, 16)
+            assert torch.equal(out, ref)
+            assert ops.grid_took_it(out) == want_grid
+    finally:
+        ops.KNN_MODE = "auto"
