@@ -217,3 +217,29 @@ def test_packer_layout_is_aligned_and_roundtrips():
     assert assemble._cumsum0([2, 0, 5]) == [0, 2, 2, 7]
     with pytest.raises(Exception):
         assemble.batch_from_data_list([], device="cuda")
+
+
+@pytest.mark.parametrize("backbone", ["TAGConv", "GCNConv", "GATConv"])
+def test_model_structure_matches_the_reference_loader(backbone):
+    """A1: the reference's own Config(configs/everyday.json) + models/model_loader.py:load_model, executed unmodified
+    (tests/golden/make_golden_loader.py -> loader.json): same network hyper-parameters, same state-dict keys and shapes,
+    same parameter count and decoder layout for the product model and for the oracle — so reference checkpoints load."""
+    import json
+    import deformcontact_b200 as dc
+    import oracle
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "loader.json")))[backbone]
+    net = dict(gold["network"])
+    assert {k: net[k] for k in dc.EVERYDAY if k != "backbone"} == {k: v for k, v in dc.EVERYDAY.items() if k != "backbone"}
+    assert {k: v for k, v in oracle.EVERYDAY.items() if k != "backbone"} == {k: net[k] for k in oracle.EVERYDAY if k != "backbone"}
+
+    class NS:
+        pass
+    cfg = NS()
+    cfg.network = NS()
+    for k, v in net.items():
+        setattr(cfg.network, k, v)
+    for model in (dc.load_model(cfg), oracle.load_model(backbone=backbone)):
+        sd = {k: list(v.shape) for k, v in model.state_dict().items()}
+        assert sd == gold["state_dict"]
+        assert sum(p.numel() for p in model.parameters()) == gold["num_parameters"]
+        assert [type(m).__name__ for m in model.decoder] == gold["decoder"]
