@@ -233,3 +233,44 @@ def test_attn_group_equals_minibatches():
         g = oracle.Batch.from_data_list([rigid[g0], rigid[g0 + 1]])
         parts.append(m(r, g).pos)
     assert_close(full, torch.cat(parts), what="attn_group vs mini-batches")
+
+
+def test_train_step_restatement_vs_reference_training_loop(golden_dir):
+    """The oracle's train step (oracle.train_step_loss + Adam, what every GPU train-step parity test compares against)
+    reproduces the reference's OWN loop: train.py:train(config) executed unmodified for one epoch over three mini-batches
+    (tests/golden/make_golden_train.py -> train_loop.pt): the three logged losses of every step, the validation loss
+    (absolute positions, train.py:100-105) and the weights the loop saved."""
+    from oracle import synthetic
+    gold = torch.load(f"{golden_dir}/train_loop.pt")
+    m = gold["meta"]
+
+    def batch(first):
+        rests, defs, rigids = [], [], []
+        for g in range(first, first + m["batch"]):
+            rest, deformed, gen = synthetic.soft_graph(g, m["nodes"], m["k"])
+            ci = int(torch.randint(0, m["nodes"], (1,), generator=gen))
+            rests.append(rest); defs.append(deformed); rigids.append(synthetic.rigid_graph(rest.pos[ci], gen))
+        return tuple(oracle.Batch.from_data_list(l) for l in (rests, rigids, defs))
+
+    torch.manual_seed(m["seed"])
+    model = oracle.load_model(hidden_dim=m["hidden"])
+    opt = torch.optim.Adam(model.parameters(), lr=m["lr"])
+    model.train()
+    for b, logged in enumerate(gold["steps"]):
+        rest, rigid, deformed = batch(b * m["batch"])
+        loss, l1, lc = oracle.train_step_loss(model, rest, rigid, deformed, lambda_gradient=m["lambda_gradient"])
+        for got, key in ((loss, "tr_loss"), (l1, "tr_mse_loss"), (lc, "tr_consistency_loss")):
+            assert abs(got.item() - logged[key]) <= 1e-6 * abs(logged[key]), (b, key, got.item(), logged[key])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    model.eval()
+    with torch.no_grad():
+        rest, rigid, deformed = batch(1000)
+        pred = model(rest, rigid)
+        val = torch.nn.functional.l1_loss(pred.pos, deformed.pos) + m["lambda_gradient"] * oracle.GradientConsistencyLoss()(pred, deformed)
+    assert abs(val.item() - gold["validation_loss"]) <= 1e-6 * abs(gold["validation_loss"])
+    sd = model.state_dict()
+    assert set(sd) == set(gold["state_dict"])
+    for k, v in gold["state_dict"].items():
+        assert torch.allclose(sd[k], v, rtol=1e-6, atol=1e-8), k
