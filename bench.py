@@ -163,7 +163,12 @@ def config_dict(args, world):
             "attention": f"reference unmasked attention applied within groups of {args.attn_group} graphs "
                          f"(= reference mini-batch of {args.attn_group}, configs/everyday.json:26), on libdcb200: tcgen05 3xTF32 GEMMs (fp32-class accuracy) + fused softmax kernels",
             "l2": "inputs larger than L2 (per-step working set > 1 GB vs 126 MB L2); no explicit flush",
-            "structure_build": "CSR pair rebuilt every step (inside the timed region)"}
+            "structure_build": "CSR pair rebuilt every step (inside the timed region)",
+            "e2e_inputs": ("raw per-sample inputs in pinned host memory (soft positions rest + deformed, graph-local int64 edge lists, "
+                           "collider contact point + force vector + force): copied every step, batches assembled on the GPU (N3: "
+                           "features, index offsets, batch vectors, collider spheres and their mesh edges), then the step, then "
+                           "the loss read back" if getattr(args, "e2e_inputs", "raw") == "raw" else
+                           "host-collated batches (features and offset edges built on the host) copied every step")}
 
 
 def run_reference(args):
