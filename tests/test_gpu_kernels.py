@@ -487,9 +487,11 @@ def test_grid_search_large_cloud_vs_oracle_and_auto_dispatch(dc):
     d = ((pos[sub, None, :] - pos[None, :, :]) ** 2)
     d2 = (d[..., 0] + d[..., 1]) + d[..., 2]                      # the oracle's association (oracle/graphs.py:_sqdist)
     d2[torch.arange(sub.numel()), sub] = float("inf")
-    want = torch.topk(d2, 16, dim=1, largest=False).indices.sort(1).values
+    vals, idx = torch.sort(d2, dim=1, stable=True)
+    clean = vals[:, 15] < vals[:, 16]                             # a tie at the k-th place is resolved by index: skip it here
+    want = idx[:, :16].sort(1).values
     tab = ei[0].cpu().reshape(40000, 16)[sub].sort(1).values
-    assert torch.equal(tab, want)
+    assert clean.sum() >= sub.numel() - 2 and torch.equal(tab[clean], want[clean])
     # batched clouds never take the grid path
     assert not ops._use_grid(40000, torch.zeros(40000, dtype=torch.long), None, 17)
 
