@@ -33,6 +33,7 @@ class Hop(C.Structure):
 
 
 MAX_CHAIN = 4
+MAX_SEGS = 4      # dc_gemm: K-segments per call (csrc/gemm.cu); ops.gemm chains larger lists
 
 _p, _i64, _i32, _f32, _sz, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t, C.c_int
 
@@ -58,7 +59,7 @@ PROTOTYPES = {
     "dc_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _int, _int]),
     "dc_gemm": (_int, [C.POINTER(GemmSeg), _int, _int, _int, _i64, _i64, _p, _i64, _p, _int, _int, _int, _p, _sz, _p]),
     "dc_gemm_batched_workspace_bytes": (_sz, [_i32]),
-    "dc_gemm_batched": (_int, [C.POINTER(GemmProblem), _i32, _int, _int, _int, _int, _p, _sz, _p]),
+    "dc_gemm_batched": (_int, [C.POINTER(GemmProblem), _i32, _int, _int, _int, _int, _p, _sz, _p, _sz, _p]),
     "dc_colsum_workspace_bytes": (_sz, [_i64, _i64]),
     "dc_colsum": (_int, [_p, _i64, _i64, _i64, _p, _p, _sz, _p]),
     "dc_edge_loss": (_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p]),

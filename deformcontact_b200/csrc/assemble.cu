@@ -123,7 +123,7 @@ instance_points_kernel(const double* __restrict__ tmpl, const double* __restrict
   }
 }
 
-inline unsigned grid_for(int64_t n) { return (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)kSMs * 16); }
+inline unsigned grid_for(int64_t n) { return (unsigned)std::min<int64_t>(cdiv(n, 256), (int64_t)sm_count() * 16); }
 }  // namespace
 
 extern "C" int dc_batch_vector(const int64_t* node_ptr, int64_t B, int64_t N, int64_t* batch, dc_stream_t stream_) {

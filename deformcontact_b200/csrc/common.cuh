@@ -57,6 +57,23 @@ struct Carver {
   size_t used() const { return align_up(off, 256); }
 };
 
-constexpr int kSMs = 148;
+constexpr int kSMs = 148;   // B200; device code only (prefetch-distance heuristics).  Host launch sites use sm_count().
+
+// SM count of the current device (queried once per device, cached).
+int sm_count();
+
+// cudaFuncSetAttribute is per device: a once-flag per (call site, device) instead of a process-wide bool, so a process
+// that drives a second GPU sets the >48 KB dynamic shared memory / carve-out attributes there too.
+struct DeviceOnce {
+  unsigned long long mask = 0;   // bit d set = done on device d (benign if raced: the attribute calls are idempotent)
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+  }
+};
 
 }  // namespace dcb

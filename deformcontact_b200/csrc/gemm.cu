@@ -14,16 +14,18 @@ int gemm_tc2(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t 
              const float* bias, int relu, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t gemm_tc2_batched_workspace_bytes(int count);
 int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int transB, int relu, int accumulate, void* workspace,
-                     size_t workspace_bytes, cudaStream_t st);
+                     size_t workspace_bytes, void* host_staging, size_t host_staging_bytes, cudaStream_t st);
 }  // namespace dcb
 
 extern "C" size_t dc_gemm_batched_workspace_bytes(int32_t count) { return dcb::gemm_tc2_batched_workspace_bytes(count); }
 
 extern "C" int dc_gemm_batched(const dc_gemm_problem* problems, int32_t count, int transA, int transB, int relu, int accumulate,
-                               void* workspace, size_t workspace_bytes, dc_stream_t stream_) {
+                               void* workspace, size_t workspace_bytes, void* host_staging, size_t host_staging_bytes,
+                               dc_stream_t stream_) {
   DC_REQUIRE(count >= 0, DC_EINVAL, "gemm_batched: negative count");
   if (count == 0) return DC_OK;
-  return dcb::gemm_tc2_batched(problems, count, transA, transB, relu, accumulate, workspace, workspace_bytes, (cudaStream_t)stream_);
+  return dcb::gemm_tc2_batched(problems, count, transA, transB, relu, accumulate, workspace, workspace_bytes, host_staging,
+                               host_staging_bytes, (cudaStream_t)stream_);
 }
 
 extern "C" size_t dc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K_total, int transA, int transB) {

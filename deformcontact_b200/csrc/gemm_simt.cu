@@ -190,8 +190,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
 
 static int plan_splits(int64_t M, int64_t N, int kb_total) {
   int64_t tiles = cdiv(M, BM) * cdiv(N, BN);
-  if (tiles >= kSMs || kb_total < 64) return 1;
-  int64_t want = cdiv(2 * kSMs, tiles);
+  if (tiles >= sm_count() || kb_total < 64) return 1;
+  int64_t want = cdiv(2 * sm_count(), tiles);
   int64_t maxs = kb_total / 16;  // at least 16 k-blocks (256 k) per split
   int64_t s = want < maxs ? want : maxs;
   return (int)(s < 1 ? 1 : s);

@@ -488,8 +488,8 @@ int make_map2(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t rows,
 
 int t2_k_parts(int64_t M, int64_t N, int64_t kb_total) {
   const int64_t mn = cdiv(M, T2_BM) * cdiv(N, T2_BN);
-  if (mn >= kSMs) return 1;
-  int64_t parts = kSMs / mn;                          // fill the machine once
+  if (mn >= sm_count()) return 1;
+  int64_t parts = sm_count() / mn;                          // fill the machine once
   const int64_t max_parts = kb_total / T2_DRAIN_KB;   // at least one full chain per part
   if (parts > max_parts) parts = max_parts;
   if (parts > T2_MAX_KPARTS) parts = T2_MAX_KPARTS;
@@ -558,12 +558,11 @@ int gemm_tc2(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t 
     DC_REQUIRE(workspace && workspace_bytes >= need, DC_EWORKSPACE, "gemm_tc2: workspace %zu < %zu", workspace_bytes, need);
     p.partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
     DC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
-    attr_set = true;
   }
-  const int grid = p.items < kSMs ? p.items : kSMs;
+  const int grid = p.items < sm_count() ? p.items : sm_count();
   gemm_tc2_kernel<<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(mA[0], mA[1], mA[2], mA[3], mB[0], mB[1], mB[2], mB[3], p);
   DC_LAUNCH_CHECK();
   if (p.k_parts > 1) {
@@ -582,17 +581,26 @@ size_t gemm_tc2_batched_workspace_bytes(int count) {
 // `count` independent single-segment problems with common transposes in ONE persistent launch: work items of all
 // problems are dealt to the CTAs round-robin, so problems that are too small to fill the machine alone (the
 // per-group attention products) run at the rate of a large one.  The problem table (tensor maps + sizes) is built
-// on the host and copied into `workspace` on the stream.
+// on the host — in `host_staging` (caller-owned PINNED memory, at least the workspace size) when given, so that the
+// upload is a truly asynchronous, CUDA-graph-capturable copy — and copied into `workspace` on the stream.
 int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int transB, int relu, int accumulate, void* workspace,
-                     size_t workspace_bytes, cudaStream_t st) {
+                     size_t workspace_bytes, void* host_staging, size_t host_staging_bytes, cudaStream_t st) {
   DC_REQUIRE(probs && count > 0, DC_EINVAL, "gemm_batched: no problems");
   const size_t need = gemm_tc2_batched_workspace_bytes(count);
   DC_REQUIRE(workspace && workspace_bytes >= need, DC_EWORKSPACE, "gemm_batched: workspace %zu < %zu", workspace_bytes, need);
   const size_t tab_bytes = align_up((size_t)count * sizeof(T2Problem), 256);
   const size_t off_bytes = (size_t)(count + 1) * sizeof(int);
   // host image of the table (tensor maps must be 64-byte aligned in device memory: the workspace is aligned to 256)
-  std::vector<unsigned char> host(tab_bytes + off_bytes + 64);
-  unsigned char* hbase = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(host.data()) + 63) & ~(uintptr_t)63);
+  std::vector<unsigned char> host;
+  unsigned char* hraw = static_cast<unsigned char*>(host_staging);
+  if (hraw) {
+    DC_REQUIRE(host_staging_bytes >= tab_bytes + off_bytes + 64, DC_EWORKSPACE, "gemm_batched: host staging %zu < %zu",
+               host_staging_bytes, tab_bytes + off_bytes + 64);
+  } else {   // legacy form: pageable image, staged by the runtime before cudaMemcpyAsync returns (NOT capturable)
+    host.resize(tab_bytes + off_bytes + 64);
+    hraw = host.data();
+  }
+  unsigned char* hbase = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(hraw) + 63) & ~(uintptr_t)63);
   T2Problem* tab = reinterpret_cast<T2Problem*>(hbase);
   int* item_off = reinterpret_cast<int*>(hbase + tab_bytes);
   int64_t items = 0;
@@ -628,7 +636,7 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
   item_off[count] = (int)items;
   if (items == 0) return DC_OK;
   unsigned char* dbase = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-  DC_CUDA(cudaMemcpyAsync(dbase, hbase, tab_bytes + off_bytes, cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+  DC_CUDA(cudaMemcpyAsync(dbase, hbase, tab_bytes + off_bytes, cudaMemcpyHostToDevice, st));   // pinned source: async / a graph copy node
   T2Params p{};
   p.batch = reinterpret_cast<const T2Problem*>(dbase);
   p.item_off = reinterpret_cast<const int*>(dbase + tab_bytes);
@@ -642,12 +650,11 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
   p.drain_kb = T2_DRAIN_KB;
   p.relu = relu; p.accumulate = accumulate;
   p.raw_hi = 1;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
     DC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
-    attr_set = true;
   }
-  const int grid = p.items < kSMs ? p.items : kSMs;
+  const int grid = p.items < sm_count() ? p.items : sm_count();
   CUtensorMap dummy{};
   gemm_tc2_kernel<<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(dummy, dummy, dummy, dummy, dummy, dummy, dummy, dummy, p);
   DC_LAUNCH_CHECK();

@@ -289,7 +289,7 @@ int build_grid(const float* pos, int64_t N, const GridWs& g, cudaStream_t st) {
   DC_CUDA(cudaMemsetAsync(g.cursor, 0, (mc + 1) * sizeof(uint32_t), st));
   bbox_partial_kernel<<<BB_BLOCKS, BB_THREADS, 0, st>>>(pos, N, g.partial);
   grid_params_kernel<<<1, 32, 0, st>>>(g.partial, BB_BLOCKS, grid_target_cells(N), mc, N, g.gp);
-  const unsigned nb = (unsigned)std::min<int64_t>(cdiv(N, 256), (int64_t)kSMs * 16);
+  const unsigned nb = (unsigned)std::min<int64_t>(cdiv(N, 256), (int64_t)sm_count() * 16);
   cell_count_kernel<<<nb, 256, 0, st>>>(pos, N, g.gp, g.cell_of, g.count);
   DC_LAUNCHED(3);
   if (int rc = exclusive_scan_u32(g.count, mc + 1, g.bsum, st)) return rc;   // unused cells keep start = N

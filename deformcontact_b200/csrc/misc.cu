@@ -247,7 +247,7 @@ extern "C" int dc_permute_rows(const float* in, int64_t ldin, const int32_t* per
   if (N == 0 || F == 0) return DC_OK;
   DC_REQUIRE(in && perm && out && in != out && ldin >= F && ldout >= F, DC_EINVAL, "permute_rows: bad args");
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(N * (int64_t)F, 256 * 4), (int64_t)kSMs * 32);
+  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(N * (int64_t)F, 256 * 4), (int64_t)sm_count() * 32);
   if (F % 4 == 0 && ldin % 4 == 0 && ldout % 4 == 0 && al16(in) && al16(out))
     permute_rows_kernel4<<<grid ? grid : 1, 256, 0, st>>>(reinterpret_cast<const float4*>(in), ldin / 4, perm,
                                                           reinterpret_cast<float4*>(out), ldout / 4, N, F / 4);

@@ -731,11 +731,10 @@ extern "C" int dc_spmm_lean(const int32_t* rowptr, const void* edges, const floa
   }
   DC_REQUIRE(n_tiles > 0, DC_EINVAL, "spmm_lean: no tiles");
   const int n_slices = (F + 31) / 32;
-  static bool carve = false;
-  if (!carve) {
+  static DeviceOnce carve;
+  if (carve.first()) {
     cudaFuncSetAttribute(spmm_lean_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(spmm_lean_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    carve = true;
   }
   const unsigned grid = (unsigned)(n_tiles * n_slices);
   if (F % 32 == 0)
@@ -784,10 +783,9 @@ extern "C" int dc_spmm_chain(const int32_t* rowptr, const void* edges, const flo
   }
   DC_REQUIRE(n_tiles > 0, DC_EINVAL, "spmm_chain: no tiles");
   const int n_slices = F / 32;
-  static bool carve = false;
-  if (!carve) {
+  static DeviceOnce carve;
+  if (carve.first()) {
     cudaFuncSetAttribute(spmm_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    carve = true;
   }
   spmm_chain_kernel<<<(unsigned)(n_tiles * n_slices), 1024, 0, st>>>(rowptr, static_cast<const int2*>(edges), self_w, a, num_hops,
                                                                      (int)N, self_loop, tile_ptr, n_slices, tile_nodes);
@@ -825,11 +823,10 @@ extern "C" int dc_spmm_tiled(const int32_t* rowptr, const int32_t* nbr, const fl
   }
   DC_REQUIRE(n_tiles > 0, DC_EINVAL, "spmm_tiled: no tiles");
   const int n_slices = (F + 31) / 32;
-  static bool carveout_set = false;  // idempotent attribute; benign if raced
-  if (!carveout_set) {
+  static DeviceOnce carveout_set;  // idempotent attribute; benign if raced
+  if (carveout_set.first()) {
     cudaFuncSetAttribute(spmm_tiled_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(spmm_tiled_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    carveout_set = true;
   }
   DC_REQUIRE(N < (1ll << 31) && (uint64_t)N * (uint64_t)ldh < (1ull << 32) && (uint64_t)N * (uint64_t)ldo < (1ull << 32) &&
                  (!add || (uint64_t)N * (uint64_t)ldadd < (1ull << 32)),
@@ -840,19 +837,17 @@ extern "C" int dc_spmm_tiled(const int32_t* rowptr, const int32_t* nbr, const fl
     if (tile_ptr) max_rows = T5_MAX_ROWS;
     if (max_rows > T5_MAX_ROWS) max_rows = T5_MAX_ROWS;
     const int smem = max_rows * 64;
-    static bool attr5 = false;
-    if (!attr5) {
+    static DeviceOnce attr5;
+    if (attr5.first()) {
       DC_CUDA(cudaFuncSetAttribute(spmm_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_MAX_ROWS * 64));
-      attr5 = true;
     }
     spmm_smem_kernel<<<(unsigned)(n_tiles * n_slices16), T5_THREADS, smem, st>>>(
         rowptr, nbr, w, self_w, h, (unsigned)ldh, out, (unsigned)ldo, add, (unsigned)ldadd, (int)N, F, self_loop, bias, relu,
         tile_ptr, n_slices16, tile_nodes);
   } else if (variant == 1 || variant == 2) {
-    static bool carve4 = false;
-    if (!carve4) {
+    static DeviceOnce carve4;
+    if (carve4.first()) {
       cudaFuncSetAttribute(spmm_tiled_prefetch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-      carve4 = true;
     }
     spmm_tiled_prefetch_kernel<<<(unsigned)(n_tiles * n_slices), T4_THREADS, 0, st>>>(
         rowptr, nbr, w, self_w, h, (unsigned)ldh, out, (unsigned)ldo, add, (unsigned)ldadd, (int)N, F, self_loop, bias, relu,

@@ -357,7 +357,7 @@ extern "C" int dc_spmm_blocks(const void* slots, const void* recs, const int32_t
   const int n_slices = (F + 31) / 32;
   const int64_t n_ts = n_tiles * n_slices;
   DC_REQUIRE(n_ts < (1ll << 31), DC_ENOSUP, "spmm_blocks: too many tile slices");
-  const unsigned grid = (flags & 1) ? (unsigned)(n_ts < kSMs ? n_ts : kSMs) : (unsigned)n_ts;
+  const unsigned grid = (flags & 1) ? (unsigned)(n_ts < sm_count() ? n_ts : sm_count()) : (unsigned)n_ts;
   const bool full = F % 32 == 0, t768 = (flags >> 2) & 1;
   const int prefetch = (flags >> 1) & 1;
   const int l2_ahead = (flags >> 3) & 3;   // 0 = off, else distance (in grid strides) of the L2 prefetch stream

@@ -5,6 +5,7 @@ allocator, enqueues on torch's current stream and returns immediately (no host s
 where a data-dependent output size must be read back: ``knn_graph`` / ``radius_graph``).
 PyTorch is plumbing here: device memory and streams.  No eager fallback exists.
 """
+import collections
 import ctypes as C
 import weakref
 
@@ -62,6 +63,42 @@ def _rows(t, name):
 
 def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+# Page-locked staging for host-built tables (dc_gemm_batched): the library fills the buffer and enqueues an asynchronous
+# upload, so the buffer must outlive the copy.  Eager: a buffer returns to the free list once an event recorded behind
+# the copy has completed.  Under CUDA-graph capture the copy becomes a node that re-reads the buffer on every replay:
+# buffers are handed to ``CAPTURE_KEEPALIVE`` (set by step.CapturedTrainStep, which owns them as long as its graph).
+_STAGE_FREE = {}
+_STAGE_BUSY = collections.deque()
+CAPTURE_KEEPALIVE = None
+
+
+def _capturing():
+    return torch.cuda.is_current_stream_capturing()
+
+
+def _staging_get(nbytes):
+    if not _capturing():
+        while _STAGE_BUSY and _STAGE_BUSY[0][0].query():
+            _, t = _STAGE_BUSY.popleft()
+            _STAGE_FREE.setdefault(t.numel(), []).append(t)
+    size = max(4096, 1 << (int(nbytes) - 1).bit_length())
+    free = _STAGE_FREE.get(size)
+    if free:
+        return free.pop()
+    return torch.empty(size, dtype=torch.uint8, pin_memory=True)
+
+
+def _staging_put(t):
+    if _capturing():
+        if CAPTURE_KEEPALIVE is None:
+            raise _abi.DcError("stream capture of a host-staged call needs ops.CAPTURE_KEEPALIVE (use step.CapturedTrainStep)")
+        CAPTURE_KEEPALIVE.append(t)
+    else:
+        ev = torch.cuda.Event()
+        ev.record()
+        _STAGE_BUSY.append((ev, t))
 
 
 # ----------------------------------------------------------------------------- K5
@@ -170,9 +207,16 @@ def _eligible_order(edge_index, num_nodes, mode, ptr_host):
     return _order_hint(edge_index, num_nodes)
 
 
+def _need_pos(pos):
+    """The C ABI reads 3 floats per point and has no dimension argument: anything but fp32 [N, 3] is an error."""
+    _need(pos, _f32, "pos")
+    if pos.dim() != 2 or pos.shape[1] != 3:
+        raise _abi.DcError(f"pos: expected [N, 3] points, got {tuple(pos.shape)}")
+
+
 def cell_order(pos):
     """int32 [N]: point indices in grid-cell order (dc_cell_order)."""
-    _need(pos, _f32, "pos")
+    _need_pos(pos)
     pos = pos.contiguous()
     N = pos.shape[0]
     order = torch.empty(N, dtype=_i32, device=pos.device)
@@ -207,6 +251,10 @@ class GraphCSR:
         if mode not in ("tag", "gcn", "gat", "plain"):
             raise ValueError(mode)
         self.mode, self.N, self.E = mode, int(num_nodes), int(edge_index.shape[1])
+        # the caller's tensor: graph_csr keys its cache on this tensor's address, so the entry must keep it alive (also on the
+        # relabelling path below, which otherwise stores only the relabelled copy) or the allocator could hand the same
+        # address to a different edge list of the same shape
+        self._src_edge_index = edge_index
         # one large graph with a registered spatial order: build everything on relabelled nodes (see REORDER above)
         self.order = _eligible_order(edge_index, self.N, mode, ptr_host) if reorder else None
         self.rank = None
@@ -324,15 +372,16 @@ _CSR_CACHE_MAX = 16
 def graph_csr(edge_index, num_nodes, mode="tag", ptr_host=None, reorder=True):
     """Structure cache: ``conv(x, edge_index)`` (models/model.py:71,77) passes the same
     ``edge_index`` tensor to every layer and hop, so the CSR pair is built once per batch.
-    Keyed on storage identity + version; the entry pins the tensor so the address cannot be
-    recycled while cached."""
+    Keyed on storage identity + version; the entry pins the caller's tensor (``GraphCSR._src_edge_index``) so
+    the address cannot be recycled while cached.  Writes to ``edge_index`` that bypass torch's version counter (raw
+    pointer writes by a kernel through ``out=``) are not seen: call ``clear_csr_cache()`` after such a write."""
     if isinstance(edge_index, GraphCSR):
         return edge_index
     reorder = bool(reorder) and _eligible_order(edge_index, int(num_nodes), mode, ptr_host) is not None
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), mode,
            edge_index.device.index, reorder)
     hit = _CSR_CACHE.get(key)
-    if hit is not None:
+    if hit is not None and hit._src_edge_index.data_ptr() == edge_index.data_ptr():
         return hit
     g = GraphCSR(edge_index, num_nodes, mode, ptr_host, reorder=reorder)
     if len(_CSR_CACHE) >= _CSR_CACHE_MAX:
@@ -509,7 +558,16 @@ def edge_relu(rowptr, nbr, p, q, r=None, mode=0):
 # ----------------------------------------------------------------------------- K2 / K3
 def gemm(segs, M, N, trans_a=False, trans_b=True, bias=None, relu=False, out=None, accumulate=False,
          precision=GEMM_AUTO):
-    """C[M,N] = act(sum_s opA(A_s) opB(B_s) + bias) (+C); segs = [(A_s, B_s), ...]; see dc_gemm."""
+    """C[M,N] = act(sum_s opA(A_s) opB(B_s) + bias) (+C); segs = [(A_s, B_s), ...]; see dc_gemm.
+    More than ``_abi.MAX_SEGS`` segments (a decoder fed by >= 4 attention heads, TAGConv with K >= 4) are chained
+    in groups with ``accumulate``; bias and ReLU are applied by the last group."""
+    if len(segs) > _abi.MAX_SEGS:
+        groups = [segs[i:i + _abi.MAX_SEGS] for i in range(0, len(segs), _abi.MAX_SEGS)]
+        for gi, grp in enumerate(groups):
+            last = gi == len(groups) - 1
+            out = gemm(grp, M, N, trans_a=trans_a, trans_b=trans_b, bias=bias if last else None, relu=relu and last, out=out,
+                       accumulate=accumulate or gi > 0, precision=precision)
+        return out
     arr = (_abi.GemmSeg * len(segs))()
     ktot = 0
     dev = segs[0][0].device
@@ -570,10 +628,12 @@ def gemm_batched(problems, trans_a=False, trans_b=True, relu=False, accumulate=F
         return
     nb = _abi.lib().dc_gemm_batched_workspace_bytes(len(problems))
     ws = _workspace(nb, problems[0][0].device)
+    stage = _staging_get(nb)
     e0 = _prof_begin()
     _abi.call("dc_gemm_batched", arr, len(problems), int(trans_a), int(trans_b), int(bool(relu)), int(bool(accumulate)), _ptr(ws), nb,
-              _stream())
+              stage.data_ptr(), stage.numel(), _stream())
     _prof_end(e0, op="gemm", M=0, N=0, K=0, flops=flops)
+    _staging_put(stage)
 
 
 def rowdot(A, B):
@@ -628,7 +688,7 @@ def _use_grid(N, batch, ptr, width):
 
 def knn_table(pos, k, batch=None, ptr=None, loop=False):
     """int32 [N, k (+1 if not loop)] neighbour table, ascending (distance, index), -1 padded."""
-    _need(pos, _f32, "pos")
+    _need_pos(pos)
     pos = pos.contiguous()
     N = pos.shape[0]
     W = k + (0 if loop else 1)
@@ -647,7 +707,7 @@ def knn_table(pos, k, batch=None, ptr=None, loop=False):
 
 
 def radius_table(pos, r, batch=None, ptr=None, loop=False, max_num_neighbors=32):
-    _need(pos, _f32, "pos")
+    _need_pos(pos)
     pos = pos.contiguous()
     N = pos.shape[0]
     W = max_num_neighbors + (0 if loop else 1)
@@ -702,7 +762,7 @@ def mesh_edges(triangles, offset=0, out=None, start=0):
 
 
 def posenc(pos, out=None, col0=0):
-    _need(pos, _f32, "pos")
+    _need_pos(pos)
     pos = pos.contiguous()
     N = pos.shape[0]
     if out is None:
@@ -767,7 +827,7 @@ def mesh_edges_batched(triangles, tri_ptr=None, node_ptr=None, num_graphs=None, 
 def node_features(pos, head=None, node_ptr=None, out=None):
     """[head[graph(n)] | to_log_freq(pos[n], 3, 1)]: the 21-d soft features (``head`` None) or the collider's
     25-d ``_feature_rigid`` (``head`` fp32 [B, 4] = force_vector | force)."""
-    _need(pos, _f32, "pos"); _need(head, _f32, "head"); _need(node_ptr, _i64, "node_ptr")
+    _need_pos(pos); _need(head, _f32, "head"); _need(node_ptr, _i64, "node_ptr")
     pos = pos.contiguous()
     N = pos.shape[0]
     H = 0 if head is None else head.shape[1]

@@ -12,7 +12,9 @@
  *  - the caller owns all memory (inputs, outputs, workspace); nothing is allocated, freed or
  *    retained past return;
  *  - all work is enqueued on `stream` (a cudaStream_t); no host synchronisation, no
- *    default-stream use, no global mutable state  => re-entrant and CUDA-graph capturable;
+ *    default-stream use, no mutable state shared between calls except a launch counter and per-device "function
+ *    attribute set" flags (both idempotent)  => re-entrant and CUDA-graph capturable.  One entry point uploads a
+ *    host-built table (dc_gemm_batched): it is capturable when the caller passes page-locked staging memory;
  *  - returns DC_OK (0) or a negative dc_status; dc_last_error() gives a thread-local message;
  *  - features / weights are fp32, indices int32 inside the ABI (int64 edge_index is converted
  *    by dc_csr_build); leading dimensions (ld*) are in elements;
@@ -200,7 +202,12 @@ DC_API int dc_gemm(const dc_gemm_seg* segs /*host array*/, int nseg, int transA,
  * problems too small to fill 148 SMs alone (the per-group products of the cross attention, models/model.py:16-18) run
  * at the rate of a large one.  Every problem must satisfy the tensor-path requirements of dc_gemm (DC_ENOSUP
  * otherwise; the caller then falls back to per-problem dc_gemm).  `problems` is a host array; the problem table
- * (tensor maps) is staged through `workspace`. */
+ * (tensor maps) is built on the host and uploaded into `workspace` on the stream.  `host_staging` (HOST pointer,
+ * page-locked, >= dc_gemm_batched_workspace_bytes(count) bytes, caller-owned) holds the host image of the table: the
+ * upload is then an asynchronous copy that CUDA-graph capture records as a copy node, and the caller must keep the
+ * buffer alive and unmodified until the copy has executed (for a captured graph: as long as the graph lives).  With
+ * host_staging = NULL the image is a temporary pageable buffer: correct, but the call then blocks the host for the
+ * staging copy and must NOT be stream-captured. */
 typedef struct {
   const float* A;
   int64_t lda;
@@ -215,7 +222,8 @@ typedef struct {
 } dc_gemm_problem;
 DC_API size_t dc_gemm_batched_workspace_bytes(int32_t count);
 DC_API int dc_gemm_batched(const dc_gemm_problem* problems /*host array*/, int32_t count, int transA, int transB, int relu,
-                           int accumulate, void* workspace, size_t workspace_bytes, dc_stream_t stream);
+                           int accumulate, void* workspace, size_t workspace_bytes, void* host_staging /*pinned host or NULL*/,
+                           size_t host_staging_bytes, dc_stream_t stream);
 
 /* colsum[n] = sum_m X[m, n] (bias gradient), deterministic two-stage tree. */
 DC_API size_t dc_colsum_workspace_bytes(int64_t M, int64_t N);

@@ -154,10 +154,9 @@ def test_graphnet_train_step_vs_oracle(dc, attn_group):
     loss_o, l1_o, lc_o = dc.train_step_loss(ours, cu(rest), cu(rigid), cu(deformed))
     loss_o.backward()
     assert_close(loss_o, loss_r, what="loss")
-    # chain of ~10 kernels each within 1e-5 of its oracle op: 5e-5 for the end-to-end gradients
+    # north_star bar: every gradient within 1e-5 of the fp32 oracle, or (fp64 arbiter) as close to fp64 as the fp32 oracle is
     for (k, pr), (_, po), (_, p64) in zip(ref.named_parameters(), ours.named_parameters(), ref64.named_parameters()):
-        if rel_err(po.grad, pr.grad) > 5e-5:
-            assert_close_arbiter(po.grad, pr.grad, p64.grad, what=f"d{k}")
+        assert_close_arbiter(po.grad, pr.grad, p64.grad, what=f"d{k}")
 
 
 @pytest.mark.parametrize("layer", ["TAGConv", "GCNConv"])
