@@ -4,16 +4,20 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one full training step of the everyday.json model on one synthetic batch per GPU
-(config C3 of BASELINE.json): structure build (CSR pair per graph batch) + forward + loss +
-backward + gradient all-reduce (N > 1) + Adam.  Weak scaling: every rank owns
-``--graphs-per-gpu`` independent graphs; no data-path collective.
+A "step" is one full training step of the everyday.json model on config C3 of BASELINE.json — ONE
+synthetic batch of 256 graphs, split over the N ranks (strong scaling; ``--scaling weak`` keeps 256 graphs per
+GPU instead): structure build (CSR pair per graph batch) + forward + loss + backward + gradient all-reduce
+(N > 1) + Adam.  Graphs are independent, so there is no data-path collective.  The step is
+captured once in a CUDA graph (deformcontact_b200/step.py) and replayed; ``--step eager`` issues it call by call.
 
 Prints ONE JSON line (rank 0).  ``value`` = device-resident inputs; ``e2e`` = same step fed from
 pinned HOST buffers through the public API with the H2D copies and the D2H loss read inside the
-timed region.  ``roofline`` = the gather/segmented-sum hop kernel (K1) timed live with CUDA
-events inside the timed steps; ``cpu_baseline`` / ``--impl reference`` = the CPU oracle (plain
-PyTorch restatement of the reference layers; real PyG is not installable) on the host cores.
+timed region.  ``roofline`` = the step's dominant kernel (K2, tcgen05 GEMM) and ``roofline_k1`` = the
+gather/segmented-sum hop kernel (K1, the north_star kernel), both timed with CUDA events around every launch;
+``dp_grad_rel_err`` (N > 1) = all-reduced gradient against rank 0's single-process gradient on the union batch;
+``c2`` / ``c4`` / ``c5`` (N = 1) = compact lines of the other BASELINE configs; ``cpu_baseline`` /
+``--impl reference`` = the CPU oracle (plain PyTorch restatement of the reference layers; real PyG is not
+installable) on the host cores.
 """
 import argparse
 import json
@@ -33,19 +37,6 @@ import torch.distributed as tdist  # noqa: E402
 METRIC = "train_step_graphs_per_sec"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one K1 hop launch from the ncu --set full capture, relative to the
-# algorithmic bytes of that launch (1040.28 MB measured vs 1069.8 MB algorithmic: edge records partly served by L2)
-K1_NCU_TRAFFIC_RATIO = 1040.28 / 1069.80
-K1_NCU_TRAFFIC_SOURCE = ("profiles/r01_ncu_spmm_v6_lean.csv (C5 hop, N=512000, E=4096000, F=256): 560.5 MB read + 479.8 MB written "
-                         "per launch, scaled by this launch's algorithmic bytes")
-# the same for a 3-hop chain launch (K1 v9): 624.4 MB read + 1538.6 MB written vs 3 x 1069.8 MB algorithmic (hops 2 and 3 read
-# rows that are still in L2)
-K1_CHAIN_NCU_TRAFFIC_RATIO = (624.36 + 1538.59) / (3 * 1069.80)
-K1_CHAIN_NCU_TRAFFIC_SOURCE = ("profiles/r01_ncu_spmm_v9_chain.csv (3-hop chain launch, C5 graph, F=256): 624.4 MB read + 1538.6 MB "
-                               "written per launch vs 3209 MB algorithmic; single-hop launches per r01_ncu_spmm_v6_lean.csv "
-                               "(1040 MB vs 1070 MB); scaled by each launch's algorithmic bytes")
-
-
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -53,16 +44,22 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train_c3", choices=["train_c3", "infer_c2", "layer_c5", "mesh_c4"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default, BASELINE C3 as written): ONE batch of --global-batch graphs split over the ranks; "
+                         "weak: --graphs-per-gpu graphs on every rank")
+    ap.add_argument("--global-batch", type=int, default=256)
     ap.add_argument("--graphs-per-gpu", type=int, default=256)
+    ap.add_argument("--step", default="graph", choices=["graph", "eager"],
+                    help="graph (default): the whole step captured once in a CUDA graph and replayed (deformcontact_b200/step.py); "
+                         "eager: one Python / ctypes call per kernel")
+    ap.add_argument("--no-all-configs", dest="all_configs", action="store_false",
+                    help="skip the compact C2 / C4 / C5 sub-benchmarks appended to the default 1-GPU line")
     ap.add_argument("--nodes", type=int, default=2000)
     ap.add_argument("--k", type=int, default=8)
     ap.add_argument("--attn-group", type=int, default=4)
     ap.add_argument("--cpu-sample-graphs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-inputs", choices=["raw", "collated"], default="raw",
-                    help="end-to-end arm: 'raw' = positions + graph-local edges + collider parameters, batch assembled on the GPU "
-                         "(N3); 'collated' = host-built batches (features, offset edges) copied as they are")
     ap.add_argument("--layer", default="tag", choices=["tag", "gcn", "gat", "mpnn"], help="C5: which layer")
     ap.add_argument("--no-tiles", action="store_true", help="C5: fixed 2048-node tiles instead of graph-aligned tiles")
     ap.add_argument("--hidden", type=int, default=256, help="C5 sweep: feature width")
@@ -155,20 +152,23 @@ def oracle_train_arm(args, steps, warmup):
 
 
 def config_dict(args, world):
-    return {"workload": f"C3 everyday.json training step: {args.graphs_per_gpu} graphs/GPU x {args.nodes} nodes kNN-{args.k} "
-                        f"(21-d) + one 762-node collider mesh graph each (25-d), TAGConv x2 per branch, hidden 256, "
-                        f"MHA 2 heads, decoder 3, L1 + consistency loss, Adam",
-            "graphs_per_gpu": args.graphs_per_gpu, "global_batch": args.graphs_per_gpu * world, "nodes_per_graph": args.nodes,
+    if args.scaling == "strong":
+        btot, per = args.global_batch, -(-args.global_batch // world)
+    else:
+        btot, per = args.graphs_per_gpu * world, args.graphs_per_gpu
+    return {"workload": f"C3 everyday.json training step: ONE batch of {btot} graphs x {args.nodes} nodes kNN-{args.k} (21-d) + one "
+                        f"762-node collider mesh graph each (25-d), data-parallel over {world} GPU(s) ({per} graphs per GPU), "
+                        f"TAGConv x2 per branch, hidden 256, MHA 2 heads, decoder 3, L1 + consistency loss, gradient all-reduce, Adam",
+            "graphs_per_gpu": per, "global_batch": btot, "nodes_per_graph": args.nodes,
             "knn_k": args.k, "parallelism": f"dp{world}",
             "attention": f"reference unmasked attention applied within groups of {args.attn_group} graphs "
                          f"(= reference mini-batch of {args.attn_group}, configs/everyday.json:26), on libdcb200: tcgen05 3xTF32 GEMMs (fp32-class accuracy) + fused softmax kernels",
             "l2": "inputs larger than L2 (per-step working set > 1 GB vs 126 MB L2); no explicit flush",
             "structure_build": "CSR pair rebuilt every step (inside the timed region)",
-            "e2e_inputs": ("raw per-sample inputs in pinned host memory (soft positions rest + deformed, graph-local int64 edge lists, "
-                           "collider contact point + force vector + force): copied every step, batches assembled on the GPU (N3: "
-                           "features, index offsets, batch vectors, collider spheres and their mesh edges), then the step, then "
-                           "the loss read back" if getattr(args, "e2e_inputs", "raw") == "raw" else
-                           "host-collated batches (features and offset edges built on the host) copied every step")}
+            "e2e_inputs": "raw per-sample inputs in pinned host memory (soft positions rest + deformed, graph-local int64 edge lists, "
+                          "collider contact point + force vector + force): copied every step into static device buffers, batches "
+                          "assembled on the GPU (N3: features, index offsets, batch vectors, collider spheres and their mesh edges), "
+                          "then the step, then the loss read back"}
 
 
 def run_reference(args):
@@ -176,17 +176,69 @@ def run_reference(args):
     if rank != 0:
         return
     cb, mean = oracle_train_arm(args, args.steps, args.warmup)
+    cfg = config_dict(args, max(args.gpus, 1))
+    # what this arm really executes per step (the CPU cannot hold the full batch: the dense attention of 256 graphs does not fit
+    # host RAM); graphs/s is comparable because the attention works in groups of `attn_group` graphs on both arms
+    cfg["reference_sample"] = (f"CPU arm: every step is a bounded sample of the workload above — {args.cpu_sample_graphs} graphs x {args.nodes} "
+                               f"nodes (+ colliders), same model / loss / optimizer, {cb['cores']} host threads; not {cfg['global_batch']} graphs")
+    cfg["step_execution"] = "plain PyTorch CPU (oracle port of the reference layers; real PyG is not installable here)"
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "graphs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": config_dict(args, max(args.gpus, 1)), "cpu_baseline": cb,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": cfg, "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------- ours
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of our kernels, from the committed `ncu --set full` capture of
+    THIS command's step (profiles/r02_ncu_traffic.json, written by scripts/ncu_traffic.py on the GPU box); {} if absent."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+    except Exception:
+        return {}
+
+
+def dp_gradient_check(dc, ddist, synthetic, rank, world, dev, attn_group):
+    """Data-parallel correctness on the hardware the scaling line is measured on: every rank runs the everyday.json model on
+    its 2 graphs of a 2*world-graph batch (300 nodes each), the flat gradient is SUM-all-reduced over NCCL, and rank 0
+    compares it with its own single-process gradient of the global-mean loss on the whole batch."""
+    per, n = 2, 300
+    torch.manual_seed(0)
+    model = dc.load_model(attn_group=2).to(dev)
+    flat = ddist.FlatGrads(model.parameters())
+    rest, rigid, deformed = synthetic.make_batch(per, n, 8, first=rank * per, device=dev)
+    ns, es = ddist.loss_shares(rest.x.shape[0], rest.edge_index.shape[1], dev)
+    pred = model(rest, rigid)
+    pred.pos = pred.pos - rest.pos
+    tgt = deformed.clone(); tgt.pos = deformed.pos - rest.pos
+    l1, lc = dc.fused_losses(pred, tgt)
+    (ns * l1 + es * lc).backward()
+    flat.all_reduce()
+    err = torch.zeros(1, dtype=torch.float64, device=dev)
+    if rank == 0:
+        torch.manual_seed(0)
+        ref = dc.load_model(attn_group=2).to(dev)
+        R, G, D = synthetic.make_batch(per * world, n, 8, first=0, device=dev)
+        dc.train_step_loss(ref, R, G, D)[0].backward()
+        refflat = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+        err[0] = ((flat.flat - refflat).abs().max() / refflat.abs().max()).double()
+    tdist.broadcast(err, 0)
+    dc.ops.clear_csr_cache()
+    return float(err.item())
+
+
 def run_ours(args):
+    import gc
     import deformcontact_b200 as dc
     from deformcontact_b200 import dist as ddist, synthetic, ops, _abi
 
@@ -194,16 +246,23 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.backends.cuda.matmul.allow_tf32 = False   # whatever still runs in torch stays true fp32
     torch.backends.cudnn.allow_tf32 = False
-    Bg = args.graphs_per_gpu
-    rest, rigid, deformed = synthetic.make_batch(Bg, args.nodes, args.k, first=rank * Bg, device=dev)
+    if args.scaling == "strong":                     # BASELINE C3: ONE batch of `global_batch` graphs split over the ranks
+        first, last = ddist.shard_range(args.global_batch, rank, world)
+        Bg, Btot = last - first, args.global_batch
+    else:                                            # weak: every rank owns graphs_per_gpu graphs
+        Bg, first, Btot = args.graphs_per_gpu, rank * args.graphs_per_gpu, args.graphs_per_gpu * world
+    args.graphs_per_gpu = Bg
+    dp_err = dp_gradient_check(dc, ddist, synthetic, rank, world, dev, args.attn_group) if world > 1 else None
+    rest, rigid, deformed = synthetic.make_batch(Bg, args.nodes, args.k, first=first, device=dev)
     torch.manual_seed(0)
     model = dc.load_model(attn_group=args.attn_group).to(dev)
     flat = ddist.FlatGrads(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=4e-4, fused=True)
-    node_share, edge_share = ddist.loss_shares(rest.x.shape[0], rest.edge_index.shape[1], dev)
+    opt = torch.optim.Adam(model.parameters(), lr=4e-4, fused=True, capturable=True)   # train.py:20
+    shares = ddist.loss_shares(rest.x.shape[0], rest.edge_index.shape[1], dev)
     lib = _abi.lib()
+    use_graph = args.step == "graph"
 
-    def step(rest_b, rigid_b, def_b):
+    def eager_step(rest_b, rigid_b, def_b):
         ops.clear_csr_cache()
         flat.zero_()
         pred = model(rest_b, rigid_b)
@@ -211,7 +270,7 @@ def run_ours(args):
         tgt = def_b.clone()
         tgt.pos = def_b.pos - rest_b.pos
         l1, lc = dc.fused_losses(pred, tgt)   # = F.l1_loss(pred.pos, tgt.pos), GradientConsistencyLoss()(pred, tgt) (train.py:47-58)
-        loss = node_share * l1 + edge_share * lc
+        loss = shares[0] * l1 + shares[1] * lc
         loss.backward()
         flat.all_reduce()
         opt.step()
@@ -235,140 +294,186 @@ def run_ours(args):
             tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
         return ms.item()
 
-    # ---- device-resident arm
-    for _ in range(max(args.warmup, 3)):
-        step(rest, rigid, deformed)
+    W = max(args.warmup, 3)
+    # ---- device-resident arm: the captured step replayed on resident inputs (or the eager step with --step eager)
+    runner, mode = None, "eager (one Python / ctypes call per kernel)"
+    if use_graph:
+        runner = dc.CapturedTrainStep(model, opt, rest, rigid, deformed, flat_grads=flat, loss_shares=shares)
+        mode = runner.mode
+        resident = runner.replay
+        launches_per_step = runner.launches_per_step
+    else:
+        resident = lambda: eager_step(rest, rigid, deformed)
+    for _ in range(W):
+        resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    prof = []
-    ops.PROFILER = prof
     l0 = lib.dc_launch_count()
-    total_ms = timed(lambda: step(rest, rigid, deformed), args.steps)
-    launches = lib.dc_launch_count() - l0
-    ops.PROFILER = None
+    total_ms = timed(resident, args.steps)
+    if not use_graph:
+        launches_per_step = (lib.dc_launch_count() - l0) // args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_step = total_ms / args.steps
-    value = Bg * world / (ms_step * 1e-3)
+    value = Btot / (ms_step * 1e-3)
+    del runner, resident
+    gc.collect(); torch.cuda.empty_cache()
 
-    # ---- roofline of the dominant HBM-bound kernel (K1 hop at hidden width), from the live events
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    # ---- per-kernel timing: the same step issued eagerly with CUDA events around every libdcb200 launch (a graph replay
+    #      cannot carry timing events); the kernels and their inputs are the ones the timed region replays
+    prof_steps = 2
+    eager_step(rest, rigid, deformed)
+    prof = []
+    ops.PROFILER = prof
+    ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ep0.record()
+    for _ in range(prof_steps):
+        eager_step(rest, rigid, deformed)
+    ep1.record()
+    torch.cuda.synchronize()
+    ops.PROFILER = None
+    peaks = _peaks()
+    traffic = _ncu_traffic()
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     hop_bytes = hop_ms = 0.0
     hop_n = hop_hops = 0
-    hop_traffic = 0.0
     gemm_flops = gemm_ms = 0.0
+    gemm_n = 0
     other = {}
     for rec in prof:
         ms = rec["e0"].elapsed_time(rec["e1"])
         if rec["op"] == "spmm" and rec["F"] == 256:
             hop_bytes += rec["bytes"]; hop_ms += ms; hop_n += 1; hop_hops += rec.get("hops", 1)
-            hop_traffic += rec["bytes"] * (K1_CHAIN_NCU_TRAFFIC_RATIO if rec.get("hops", 1) > 1 else K1_NCU_TRAFFIC_RATIO)
         elif rec["op"] == "gemm":
-            gemm_flops += rec["flops"]; gemm_ms += ms
+            gemm_flops += rec["flops"]; gemm_ms += ms; gemm_n += 1
         other[rec["op"]] = other.get(rec["op"], 0.0) + ms
-    roofline = None
-    if hop_n:
-        ach = hop_bytes / (hop_ms * 1e-3) / 1e9
-        roofline = {"kernel": f"K1 gather/segmented-sum hop, F=256 ({ops.K1_VARIANT} variant)", "bound": "hbm",
-                    "achieved": ach, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": hop_traffic / hop_n, "traffic_source": K1_CHAIN_NCU_TRAFFIC_SOURCE,
-                    "launches": hop_n // args.steps, "hops": hop_hops // args.steps, "avg_launch_ms": hop_ms / hop_n,
-                    "avg_hop_ms": hop_ms / hop_hops,
-                    "algorithmic_bytes_per_launch": hop_bytes / hop_n,
-                    "share_of_step": hop_ms / total_ms,
-                    "note": "bytes = 8NF+4E+8N+4 per hop (+4NF when a fused addend is read), summed over the hops of a chain "
-                            "launch (K1 v9: the 3 hops of a TAGConv layer in one launch); timed with CUDA events around each "
-                            "launch inside the timed steps"}
-    extra = {"our_kernel_ms_per_step": {k: v / args.steps for k, v in other.items()}}
+    timing_note = (f"timed with CUDA events around each launch in {prof_steps} eager passes of the same step on the same inputs, run "
+                   "right after the timed graph replays (a replayed graph cannot carry per-kernel events)")
+    roofline = roofline_k1 = None
     if gemm_ms:
         tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
         tpeak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
-        # second roofline object: the tensor-bound kernel (K2, tcgen05 3xTF32) is where the step's time goes
-        extra["roofline_tensor"] = {
-            "kernel": "K2 dc_gemm (tcgen05 kind::tf32, 3-term split): encoder layer, attention and decoder products",
+        tr = traffic.get("gemm_tc2_kernel", {})
+        roofline = {
+            "kernel": "K2 gemm_tc2_kernel (tcgen05 kind::tf32, 3-term split): encoder layer, attention and decoder products — "
+                      "the step's dominant kernel",
             "bound": "tensor", "achieved": tf, "peak": tpeak, "peak_source": "measured dense bf16 (sustained)" if tpeak else None,
-            "unit": "TFLOP/s", "frac": (tf / tpeak) if tpeak else None, "traffic": None,
-            "ms_per_step": gemm_ms / args.steps, "share_of_step": gemm_ms / total_ms,
-            "note": "achieved = algorithmic 2*M*N*K flops / CUDA-event time of every dc_gemm launch in the timed steps (incl. the "
-                    "small fp32-SIMT ones); kind::tf32 runs at half the bf16 rate and the fp32-accurate split issues 3 MMAs per "
-                    "product, so tensor-pipe occupancy is about 6x this fraction"}
+            "unit": "TFLOP/s", "frac": (tf / tpeak) if tpeak else None,
+            "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
+            "launches": gemm_n // prof_steps, "avg_launch_ms": gemm_ms / gemm_n,
+            "algorithmic_flops_per_launch": gemm_flops / gemm_n, "share_of_step": gemm_ms / prof_steps / ms_step,
+            "note": "achieved = algorithmic 2*M*N*K flops of every dc_gemm / dc_gemm_batched call / its CUDA-event time (incl. the small "
+                    "fp32-SIMT ones); kind::tf32 runs at half the bf16 rate and the fp32-accurate split issues 3 MMAs per product, so "
+                    "the ceiling of this fraction is 1/6; " + timing_note}
+    if hop_n:
+        ach = hop_bytes / (hop_ms * 1e-3) / 1e9
+        tr = traffic.get("spmm_chain_kernel", {})
+        roofline_k1 = {"kernel": f"K1 gather/segmented-sum hop chains, F=256 ({ops.K1_VARIANT} variant) — the north_star kernel",
+                       "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / hbm_peak,
+                       "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
+                       "launches": hop_n // prof_steps, "hops": hop_hops // prof_steps, "avg_launch_ms": hop_ms / hop_n,
+                       "avg_hop_ms": hop_ms / hop_hops, "algorithmic_bytes_per_launch": hop_bytes / hop_n,
+                       "share_of_step": hop_ms / prof_steps / ms_step,
+                       "note": "bytes = 8NF+4E+8N+4 per hop (+4NF when a fused addend is read), summed over the hops of a chain launch; "
+                               + timing_note}
+    extra = {"our_kernel_ms_per_step": {k: v / prof_steps for k, v in other.items()},
+             "eager_step_ms": ep0.elapsed_time(ep1) / prof_steps}
     E_local = rest.edge_index.shape[1] + rigid.edge_index.shape[1]
-    extra["edge_traversals_per_sec"] = (2 * 3 * 2) * E_local * world / (ms_step * 1e-3)  # 2 layers x 3 hops x (fwd+bwd)
+    E_tot = torch.tensor([float(E_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tdist.all_reduce(E_tot)
+    extra["edge_traversals_per_sec"] = (2 * 3 * 2) * E_tot.item() / (ms_step * 1e-3)  # 2 layers x 3 hops x (fwd+bwd)
 
     # ---- end-to-end arm: pinned host inputs -> H2D -> (N3 batch assembly on the GPU) -> step -> D2H loss
     e2e = None
     if not args.no_e2e:
         loss_host = torch.zeros(1).pin_memory()
-        if args.e2e_inputs == "collated":
-            # the batches exactly as the reference's host-side from_data_list leaves them (features and offset edges built on the host)
-            host = {k: v.cpu().pin_memory() for k, v in dict(rx=rest.x, rp=rest.pos, dp=deformed.pos, re=rest.edge_index,
-                                                             gx=rigid.x, gp=rigid.pos, ge=rigid.edge_index, rptr=rest.ptr,
-                                                             gptr=rigid.ptr).items()}
+        eptr_l = (rest._edge_ptr if rest._edge_ptr is not None else
+                  [0] + torch.bincount(rest.batch[rest.edge_index[1]], minlength=Bg).cumsum(0).tolist())
+        local_e = rest.edge_index - rest.ptr[:-1][rest.batch[rest.edge_index[1]]]
+        # raw per-sample inputs, packed by the loader: positions, graph-local edge lists, collider contact point + force;
+        # features, index offsets, batch vectors, collider spheres and their mesh edges are produced on the GPU (N3)
+        raw_dev = {"rp": rest.pos, "dp": deformed.pos, "le": local_e, "nptr": rest.ptr, "eptr": torch.tensor(eptr_l, dtype=torch.long, device=dev),
+                   "centers": rigid._centers.to(dev), "head": rigid._head.to(dev).float()}
+        host = {k: v.cpu().contiguous().pin_memory() for k, v in raw_dev.items()}
+        nptr_l = list(rest._ptr_host)
 
-            def assemble_step():
-                d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-                rb = dc.Batch(x=d["rx"], edge_index=d["re"], pos=d["rp"]); rb.ptr = d["rptr"]; rb._ptr_host = rest._ptr_host
-                db = dc.Batch(x=d["rx"], edge_index=d["re"], pos=d["dp"]); db.ptr = d["rptr"]
-                gb = dc.Batch(x=d["gx"], edge_index=d["ge"], pos=d["gp"]); gb.ptr = d["gptr"]; gb._ptr_host = rigid._ptr_host
-                return rb, gb, db
-        else:
-            # raw per-sample inputs, packed by the loader: positions, graph-local edge lists, collider contact point + force;
-            # features, index offsets, batch vectors, collider spheres and their mesh edges are produced on the GPU (N3)
-            eptr = torch.tensor(rest._edge_ptr if rest._edge_ptr is not None else
-                                [0] + torch.bincount(rest.batch[rest.edge_index[1]], minlength=Bg).cumsum(0).tolist(), dtype=torch.long)
-            local = rest.edge_index - rest.ptr[:-1][rest.batch[rest.edge_index[1]]]
-            host = {"rp": rest.pos, "dp": deformed.pos, "le": local, "nptr": rest.ptr, "eptr": eptr,
-                    "centers": rigid._centers, "fvec": rigid._head[:, 0:3], "force": rigid._head[:, 3]}
-            host = {k: v.cpu().contiguous().pin_memory() for k, v in host.items()}
+        def assemble(raw):
+            rb = dc.graph_batch_packed(raw["rp"], raw["le"], raw["nptr"], raw["eptr"], device=dev, node_ptr_host=nptr_l, edge_ptr_host=eptr_l)
+            db = dc.Batch(x=rb.x, edge_index=rb.edge_index, pos=raw["dp"]); db.ptr = rb.ptr
+            gb = dc.collider_batch_device(raw["centers"], raw["head"])
+            return rb, gb, db
 
-            def assemble_step():
-                rb = dc.graph_batch_packed(host["rp"], host["le"], host["nptr"], host["eptr"], device=dev)
-                db = dc.Batch(x=rb.x, edge_index=rb.edge_index, pos=host["dp"].to(dev, non_blocking=True)); db.ptr = rb.ptr
-                gb = dc.collider_batch(host["centers"], host["fvec"], host["force"], device=dev)
-                return rb, gb, db
-
-            rb, gb, _ = assemble_step()   # the assembled batches must be the device-resident ones (indices and positions bit for bit)
-            n3_ok = bool(torch.equal(rb.edge_index, rest.edge_index) and torch.equal(rb.pos, rest.pos)
-                         and torch.equal(gb.edge_index, rigid.edge_index) and torch.equal(gb.pos, rigid.pos)
-                         and (rb.x - rest.x).abs().max().item() <= 1e-6 and (gb.x - rigid.x).abs().max().item() <= 1e-6)
-            if not n3_ok:
-                print("WARNING: N3-assembled batch differs from the device-resident batch", file=sys.stderr, flush=True)
+        rb, gb, _ = assemble(raw_dev)   # the assembled batches must be the device-resident ones (indices and positions bit for bit)
+        n3_ok = bool(torch.equal(rb.edge_index, rest.edge_index) and torch.equal(rb.pos, rest.pos)
+                     and torch.equal(gb.edge_index, rigid.edge_index) and torch.equal(gb.pos, rigid.pos)
+                     and (rb.x - rest.x).abs().max().item() <= 1e-6 and (gb.x - rigid.x).abs().max().item() <= 1e-6)
+        if not n3_ok:
+            print("WARNING: N3-assembled batch differs from the device-resident batch", file=sys.stderr, flush=True)
+        del rb, gb
         h2d = sum(v.numel() * v.element_size() for v in host.values())
+        if use_graph:
+            runner = dc.CapturedTrainStep(model, opt, raw=raw_dev, assemble=assemble, flat_grads=flat, loss_shares=shares)
 
-        def e2e_step():
-            rb, gb, db = assemble_step()
-            loss = step(rb, gb, db)
-            loss_host.copy_(loss.detach().reshape(1), non_blocking=False)   # D2H read of the step's result
-
-        for _ in range(2):
+            def e2e_step():
+                runner.load(raw=host)                                     # H2D of this step's raw inputs into the static buffers
+                loss = runner.replay()[0]
+                loss_host.copy_(loss.reshape(1), non_blocking=False)      # D2H read of the step's result
+        else:
+            def e2e_step():
+                loss = eager_step(*assemble({k: v.to(dev, non_blocking=True) for k, v in host.items()}))
+                loss_host.copy_(loss.detach().reshape(1), non_blocking=False)
+        for _ in range(3):
             e2e_step()
         e2e_ms = timed(e2e_step, args.steps) / args.steps
-        e2e = {"value": Bg * world / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "inputs": args.e2e_inputs}
-        if args.e2e_inputs == "raw":
-            e2e["assembled_batch_equals_resident"] = n3_ok
+        e2e = {"value": Btot / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "inputs": "raw", "assembled_batch_equals_resident": n3_ok}
+        runner = None
+        gc.collect(); torch.cuda.empty_cache()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline, _ = oracle_train_arm(args, 20, 3)
 
+    subs = {}
+    if rank == 0 and world == 1 and args.all_configs:
+        # the other BASELINE configs, compact, so that every config has a number from this run (full lines: --workload ...)
+        del model, opt, flat, rest, rigid, deformed
+        ops.clear_csr_cache(); gc.collect(); torch.cuda.empty_cache()
+        for key, fn in (("c2", run_infer_c2), ("c4", run_mesh_c4), ("c5", run_layer)):
+            try:
+                sub_args = argparse.Namespace(**vars(args))
+                sub_args.steps, sub_args.warmup = (5 if key != "c5" else 10), 3
+                sub_args.edges, sub_args.hidden, sub_args.layer, sub_args.no_tiles = 4096000.0, 256, "tag", False
+                d = fn(sub_args, emit=False)
+                keep = ("metric", "value", "unit", "ms_per_step", "higher_is_better", "gpu_launches", "clocks", "e2e", "fwd_ms",
+                        "knn_build_ms", "mp_15_layers_ms", "encoder_only_ms", "hop")
+                subs[key] = {k: d[k] for k in keep if k in d}
+                subs[key]["workload"] = d["config"]["workload"]
+                if d.get("roofline"):
+                    subs[key]["roofline"] = {k: d["roofline"][k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic")}
+            except Exception as e:   # a sub-benchmark must never take the headline line down
+                subs[key] = {"error": repr(e)[:300]}
+            ops.clear_csr_cache(); gc.collect(); torch.cuda.empty_cache()
+
     if rank == 0:
+        cfg = config_dict(args, world)
+        cfg.update({"global_batch": Btot, "step_execution": mode})
         line = {"metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config_dict(args, world),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
+                "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": cfg,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
+                "gpu_launches_per_step": int(launches_per_step), "roofline": roofline, "roofline_k1": roofline_k1,
                 "cpu_baseline": cpu_baseline, **extra}
+        if dp_err is not None:
+            line["dp_grad_rel_err"] = dp_err
+        line.update(subs)
         print(json.dumps(line), flush=True)
     if world > 1:
         tdist.destroy_process_group()
 
 
-def run_layer(args):
+def run_layer(args, emit=True):
     """C5 microbench: one TAGConv layer (F -> F, K=3) on a block-diagonal batch of kNN graphs with
     `--edges` edges in total; reports MP-layer edges/sec (fwd+bwd) and the hop kernel's roofline."""
     import deformcontact_b200 as dc
@@ -427,6 +532,7 @@ def run_layer(args):
     clocks = sampler.stop()
     hop_bytes = 8 * N * F + 4 * E + 8 * N + 4
     chained = ops.K1_CHAIN >= 1 and G.tiles_closed and F % 32 == 0
+    tr = _ncu_traffic().get("spmm_chain_kernel_c5", {})   # ncu --set full capture of exactly this launch (scripts/gpu_round.sh)
     ach = (3 * hop_bytes / (chain_ms * 1e-3) / 1e9) if chained else (hop_bytes / (hop_ms * 1e-3) / 1e9)
     line = {"metric": "mp_layer_edges_per_sec", "value": E / (fb_ms * 1e-3), "unit": "edges/s", "n_gpus": 1,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": fb_ms, "higher_is_better": True,
@@ -442,11 +548,13 @@ def run_layer(args):
                                     else f"K1 hop ({ops.K1_VARIANT})"),
                          "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": peak_src,
                          "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": (K1_CHAIN_NCU_TRAFFIC_RATIO * 3 * hop_bytes) if chained else (K1_NCU_TRAFFIC_RATIO * hop_bytes),
-                         "traffic_source": K1_CHAIN_NCU_TRAFFIC_SOURCE if chained else K1_NCU_TRAFFIC_SOURCE,
+                         "traffic": tr.get("dram_bytes_per_launch") if (chained and N == 512000 and F == 256 and k == 8) else None,
+                         "traffic_source": tr.get("source") if (chained and N == 512000 and F == 256 and k == 8) else None,
                          "algorithmic_bytes_per_launch": (3 if chained else 1) * hop_bytes,
                          "avg_launch_ms": chain_ms if chained else hop_ms}}
-    print(json.dumps(line), flush=True)
+    if emit:
+        print(json.dumps(line), flush=True)
+    return line
 
 
 def _ev_time(fn, reps, warmup=3):
@@ -479,7 +587,7 @@ def _ev_median(fn, reps, warmup=2):
     return statistics.median(ts)
 
 
-def run_infer_c2(args):
+def run_infer_c2(args, emit=True):
     """C2: everyday.json model inference, batch 64 synthetic meshes x ~5k nodes, 1 GPU."""
     import deformcontact_b200 as dc
     from deformcontact_b200 import synthetic, ops
@@ -507,18 +615,43 @@ def run_infer_c2(args):
     ms = _ev_time(step, args.steps, max(args.warmup, 3))
     launches = (lib.dc_launch_count() - l0) // (args.steps + max(args.warmup, 3))
     enc_ms = _ev_time(enc, args.steps, max(args.warmup, 3))
+    # end-to-end: raw per-sample inputs in pinned host memory -> H2D -> batch assembly on the GPU (N3) -> model -> predicted
+    # positions read back (eval.py:107-111 plus the D2H a caller needs to use the result)
+    eptr_l = (rest._edge_ptr if rest._edge_ptr is not None else
+              [0] + torch.bincount(rest.batch[rest.edge_index[1]], minlength=B).cumsum(0).tolist())
+    local_e = rest.edge_index - rest.ptr[:-1][rest.batch[rest.edge_index[1]]]
+    host = {"rp": rest.pos, "le": local_e, "nptr": rest.ptr, "eptr": torch.tensor(eptr_l, dtype=torch.long),
+            "centers": rigid._centers, "fvec": rigid._head[:, 0:3], "force": rigid._head[:, 3]}
+    host = {k: v.cpu().contiguous().pin_memory() for k, v in host.items()}
+    pos_host = torch.empty((B * n, 3), dtype=torch.float32).pin_memory()
+    nptr_l = list(rest._ptr_host)
+
+    def e2e_step():
+        ops.clear_csr_cache()
+        rb = dc.graph_batch_packed(host["rp"], host["le"], host["nptr"], host["eptr"], device=dev, node_ptr_host=nptr_l, edge_ptr_host=eptr_l)
+        gb = dc.collider_batch(host["centers"], host["fvec"], host["force"], device=dev)
+        with torch.no_grad():
+            pos_host.copy_(model(rb, gb).pos, non_blocking=False)
+    e2e_ms = _ev_time(e2e_step, args.steps, 3)
+    ok = bool(torch.equal(pos_host.to(dev), step()))
     clocks = sampler.stop()
     E = rest.edge_index.shape[1] + rigid.edge_index.shape[1]
-    print(json.dumps({"metric": "inference_graphs_per_sec", "value": B / (ms * 1e-3), "unit": "graphs/s", "n_gpus": 1,
-                      "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-                      "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-                      "config": {"workload": f"C2 everyday.json inference, {B} graphs x {n} nodes kNN-{args.k} + colliders",
-                                 "attention": f"groups of {args.attn_group}", "l2": "inputs larger than L2"},
-                      "clocks": clocks, "gpu_launches": int(launches), "encoder_only_ms": enc_ms,
-                      "encoder_edge_traversals_per_sec": 6 * E / (enc_ms * 1e-3)}), flush=True)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    line = {"metric": "inference_graphs_per_sec", "value": B / (ms * 1e-3), "unit": "graphs/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"C2 everyday.json inference, {B} graphs x {n} nodes kNN-{args.k} + colliders",
+                       "attention": f"groups of {args.attn_group}", "l2": "inputs larger than L2"},
+            "clocks": clocks, "gpu_launches": int(launches), "encoder_only_ms": enc_ms,
+            "e2e": {"value": B / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": pos_host.numel() * 4, "result_equals_resident": ok},
+            "encoder_edge_traversals_per_sec": 6 * E / (enc_ms * 1e-3)}
+    if emit:
+        print(json.dumps(line), flush=True)
+    return line
 
 
-def run_mesh_c4(args):
+def run_mesh_c4(args, emit=True):
     """C4: one 200k-node point set: kNN-16 graph build + 15 TAGConv layers (21->256, 14 x 256->256), forward."""
     import deformcontact_b200 as dc
     from deformcontact_b200 import ops
@@ -552,7 +685,7 @@ def run_mesh_c4(args):
     launches = (dc._abi.lib().dc_launch_count() - l0) // (args.steps + max(args.warmup, 3))
     clocks = sampler.stop()
     E = ei.shape[1]
-    print(json.dumps({"metric": "mesh_pass_ms", "value": knn_ms + mp_ms, "unit": "ms", "n_gpus": 1, "steps": args.steps,
+    line = ({"metric": "mesh_pass_ms", "value": knn_ms + mp_ms, "unit": "ms", "n_gpus": 1, "steps": args.steps,
                       "warmup": max(args.warmup, 3), "ms_per_step": knn_ms + mp_ms, "higher_is_better": False, "scaling": "weak",
                       "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
                       "config": {"workload": f"C4 single point set N={N}, kNN k={k} build + {L} TAGConv layers forward (45 hops), "
@@ -565,7 +698,10 @@ def run_mesh_c4(args):
                       "mp_15_layers_ms": mp_ms,
                       "radius_build_ms": radius_ms, "radius": radius, "radius_edges": int(radius_edges),
 
-                      "edge_traversals_per_sec": 3 * L * E / (mp_ms * 1e-3)}), flush=True)
+                      "edge_traversals_per_sec": 3 * L * E / (mp_ms * 1e-3)})
+    if emit:
+        print(json.dumps(line), flush=True)
+    return line
 
 
 def main():

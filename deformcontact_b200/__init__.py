@@ -11,9 +11,11 @@ from . import ops  # noqa: E402
 from .data import Data, Batch, collate_fn  # noqa: E402,F401
 from .layers import TAGConv, GCNConv, GATConv, MPNNLayer  # noqa: E402,F401
 from .graph import mesh_to_graph, knn_graph, radius_graph, construct_graph, to_log_freq  # noqa: E402,F401
-from .assemble import (batch_from_data_list, mesh_batch, collider_batch, graph_batch, graph_batch_packed,  # noqa: E402,F401
-                       Staging)
+from .assemble import (batch_from_data_list, mesh_batch, collider_batch, collider_batch_device, graph_batch,  # noqa: E402,F401
+                       graph_batch_packed, Staging)
 from .model import (GraphNet, MultiHeadAttention, GradientConsistencyLoss, load_model,  # noqa: E402,F401
                     train_step_loss, fused_losses, EVERYDAY)
 
-__version__ = "0.1.0"
+from .step import CapturedTrainStep  # noqa: E402,F401
+
+__version__ = "0.2.0"

@@ -246,13 +246,32 @@ def graph_batch(positions, edge_indices, device="cuda", encode=True, staging=Non
     return _finish(out, dv["node_ptr"], node_ptr, edge_ptr, nbytes)
 
 
-def graph_batch_packed(pos, local_edge_index, node_ptr, edge_ptr, device="cuda", encode=True):
+def graph_batch_packed(pos, local_edge_index, node_ptr, edge_ptr, device="cuda", encode=True, node_ptr_host=None,
+                       edge_ptr_host=None):
     """Same as ``graph_batch`` for inputs a loader already packed: ``pos`` [N, 3] fp32 and ``local_edge_index``
     [2, E] (graph-local, int32 / int64) in PINNED host memory, ``node_ptr`` / ``edge_ptr`` int64 [B+1] pinned tensors.
-    The arrays are copied as they are (no staging pass); offsets, ``batch`` and features are produced on the GPU."""
+    The arrays are copied as they are (no staging pass); offsets, ``batch`` and features are produced on the GPU.
+    The four arrays may also already be on the device (static input buffers of a captured step): pass the two offset
+    tables as host lists too (``node_ptr_host`` / ``edge_ptr_host``) so that nothing is read back."""
     if torch.device(device).type != "cuda":
         raise _abi.DcError("batch assembly runs on a CUDA device (libdcb200 has no CPU path)")
     d_pos, d_ei, d_np, d_ep = (t.to(device, non_blocking=True) for t in (pos, local_edge_index, node_ptr, edge_ptr))
     out = Batch(x=ops.node_features(d_pos) if encode else d_pos, pos=d_pos, edge_index=ops.edges_offset(d_ei, d_ep, d_np))
     nbytes = sum(t.numel() * t.element_size() for t in (pos, local_edge_index, node_ptr, edge_ptr))
-    return _finish(out, d_np, node_ptr.tolist(), edge_ptr.tolist(), nbytes)
+    return _finish(out, d_np, node_ptr.tolist() if node_ptr_host is None else list(node_ptr_host),
+                   edge_ptr.tolist() if edge_ptr_host is None else list(edge_ptr_host), nbytes)
+
+
+def collider_batch_device(centers, head, radius=0.05, resolution=20):
+    """``collider_batch`` for parameters that are already on the device (static input buffers of a captured step):
+    ``centers`` fp64 [B, 3], ``head`` fp32 [B, 4] = force_vector | force.  No copy, no host read."""
+    ops._need(centers, torch.float64, "centers"); ops._need(head, torch.float32, "head")
+    dev = centers.device
+    B = centers.shape[0]
+    tv, tt = _sphere_template(radius, resolution, dev)
+    V, T = tv.shape[0], tt.shape[0]
+    node_ptr = [g * V for g in range(B + 1)]
+    d_np = ops._device_table(("arange", B + 1, V), lambda: torch.tensor(node_ptr, dtype=torch.int64), dev)
+    pos = ops.instance_points(tv, centers)
+    out = Batch(x=ops.node_features(pos, head, d_np), pos=pos, edge_index=ops.mesh_edges_batched(tt, num_graphs=B, nodes_per_graph=V))
+    return _finish(out, d_np, node_ptr, [g * 3 * T for g in range(B + 1)], 0)

@@ -144,6 +144,29 @@ K1_FLAGS = int(os.environ.get("DCB200_K1_FLAGS", "28"))
 K1_CHAIN = int(os.environ.get("DCB200_K1_CHAIN", "2"))
 
 
+# Small host-built index tables (tile boundaries) uploaded once per distinct content and kept on the device: batches of a
+# training run repeat a handful of shapes, and a pageable upload inside the step would block the host — and cannot be
+# stream-captured (step.CapturedTrainStep warms the cache before it captures).
+_TABLE_CACHE = collections.OrderedDict()
+_TABLE_CACHE_MAX = 64
+
+
+def _device_table(key, build, device):
+    dev = torch.device(device)
+    full = (key, dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    hit = _TABLE_CACHE.get(full)
+    if hit is not None:
+        _TABLE_CACHE.move_to_end(full)
+        return hit
+    if _capturing():
+        raise _abi.DcError("index table missing from the device cache during stream capture (run the step once eagerly first)")
+    t = build().to(dev)
+    _TABLE_CACHE[full] = t
+    if len(_TABLE_CACHE) > _TABLE_CACHE_MAX:
+        _TABLE_CACHE.popitem(last=False)
+    return t
+
+
 def make_tiles(ptr_host, num_nodes, target=TILE_NODES):
     """Tile boundaries for dc_spmm_tiled: whole graphs of the block-diagonal batch, small graphs
     merged up to ~target receivers, large graphs split into target-sized chunks."""
@@ -274,7 +297,8 @@ class GraphCSR:
         self._wt = None
         self._edges_t = None
         tiles = make_tiles(ptr_host, self.N)
-        self.tile_ptr = (torch.tensor(tiles, dtype=_i32, device=edge_index.device) if tiles is not None else None)
+        self.tile_ptr = (_device_table(("tiles", tuple(tiles)), lambda: torch.tensor(tiles, dtype=_i32), edge_index.device)
+                         if tiles is not None else None)
         self.n_tiles = len(tiles) - 1 if tiles is not None else 0
         self._tiles_host = tiles
         # every tile boundary is a graph boundary <=> tiles are closed under the edges (needed by the hop chain)
@@ -450,7 +474,7 @@ class EdgeBlocks:
         np.cumsum((np.diff(tp) + unit - 1) // unit, out=tup[1:])
         self.max_tile_rows = int(np.diff(tp).max()) if len(tp) > 1 else 0
         self.n_tiles, self.n_units = len(tp) - 1, int(tup[-1])
-        both = torch.from_numpy(np.stack([tp, tup]).astype(np.int32)).to(dev)
+        both = _device_table(("blocks", unit, tp.tobytes()), lambda: torch.from_numpy(np.stack([tp, tup]).astype(np.int32)), dev)
         self.tile_ptr, self.tile_unit_ptr = both[0], both[1]
         cap = int(_abi.lib().dc_blocks_record_capacity(N, int(num_edges), self.n_tiles))
         self.slots = torch.empty((max(self.n_units, 1) * unit, 4), dtype=_i32, device=dev)

@@ -243,3 +243,29 @@ def test_model_structure_matches_the_reference_loader(backbone):
         assert sd == gold["state_dict"]
         assert sum(p.numel() for p in model.parameters()) == gold["num_parameters"]
         assert [type(m).__name__ for m in model.decoder] == gold["decoder"]
+
+
+def test_bench_strong_scaling_shards_one_batch():
+    """bench.py --scaling strong (default): BASELINE C3 = ONE batch of 256 graphs split over the ranks; the per-rank ranges
+    tile the batch exactly and the config says so on both arms."""
+    import argparse
+    import bench
+    from deformcontact_b200 import dist
+    for world in (1, 2, 4, 8):
+        got = [dist.shard_range(256, r, world) for r in range(world)]
+        assert got[0][0] == 0 and got[-1][1] == 256
+        assert all(a[1] == b[0] for a, b in zip(got[:-1], got[1:]))
+        assert all(hi - lo == 256 // world for lo, hi in got)
+        args = argparse.Namespace(scaling="strong", global_batch=256, graphs_per_gpu=256, nodes=2000, k=8, attn_group=4)
+        cfg = bench.config_dict(args, world)
+        assert cfg["global_batch"] == 256 and cfg["graphs_per_gpu"] == 256 // world and cfg["parallelism"] == f"dp{world}"
+    args = argparse.Namespace(scaling="weak", global_batch=256, graphs_per_gpu=64, nodes=2000, k=8, attn_group=4)
+    assert bench.config_dict(args, 4)["global_batch"] == 256
+
+
+def test_gemm_segment_chunks_cover_every_segment():
+    """ops.gemm chains more than _abi.MAX_SEGS K-segments in groups (decoder fed by >= 4 attention heads, TAGConv K >= 4)."""
+    from deformcontact_b200 import _abi
+    for n in range(1, 12):
+        groups = [list(range(n))[i:i + _abi.MAX_SEGS] for i in range(0, n, _abi.MAX_SEGS)]
+        assert sum(groups, []) == list(range(n)) and all(1 <= len(g) <= _abi.MAX_SEGS for g in groups)
