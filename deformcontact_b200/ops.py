@@ -142,6 +142,8 @@ K1_VARIANT = os.environ.get("DCB200_K1", "auto")
 K1_FLAGS = int(os.environ.get("DCB200_K1_FLAGS", "28"))
 # hop chain (K1 v9): 0 = one launch per hop; 1 = chain the forward hops of a layer; 2 = forward and backward chains
 K1_CHAIN = int(os.environ.get("DCB200_K1_CHAIN", "2"))
+# K1 v10: hop chains with the tile slice staged in shared memory by TMA (dc_spmm_stage) where the tile fits; 0 = v9 chain
+K1_STAGE = int(os.environ.get("DCB200_K1_STAGE", "1"))
 
 
 # Small host-built index tables (tile boundaries) uploaded once per distinct content and kept on the device: batches of a
@@ -368,13 +370,14 @@ def propagate_chain(g, hops, transpose=False, internal=False):
     if g.order is not None and not internal:
         return [g.propagate(h, transpose=transpose, add=a, out=o) for h, a, o in hops]
     F = hops[0][0].shape[1]
-    ok = (K1_CHAIN and g.mode in ("tag", "gcn") and g.tiles_closed and F % 32 == 0 and len(hops) <= _abi.MAX_CHAIN
+    ok = (K1_CHAIN and g.mode in ("tag", "gcn") and g.tiles_closed and len(hops) <= _abi.MAX_CHAIN
           and K1_VARIANT in ("auto", "lean", "blocks") and all(_tiled_ok(h, o, a, None) for h, a, o in hops))
-    if not ok:
+    staged = ok and K1_STAGE and g.E > 0 and _abi.lib().dc_spmm_stage_supported(g._max_tile, F)
+    if not (staged or (ok and F % 32 == 0)):
         return [g.propagate(h, transpose=transpose, add=a, out=o, internal=True) for h, a, o in hops]
     rp = g.t[0] if transpose else g.rowptr
     return spmm_chain(rp, g._edges_t if transpose else g.edges, g.self_w if g.mode == "gcn" else None, hops,
-                      self_loop=g.mode == "gcn", tile_ptr=g.tile_ptr, n_tiles=g.n_tiles)
+                      self_loop=g.mode == "gcn", tile_ptr=g.tile_ptr, n_tiles=g.n_tiles, max_tile_rows=g._max_tile if staged else 0)
 
 
 def _tiled_ok(h, out, add, bias):
@@ -526,9 +529,10 @@ def spmm_lean(rowptr, edges, self_w, h, add=None, self_loop=False, bias=None, re
     return out
 
 
-def spmm_chain(rowptr, edges, self_w, hops, self_loop=False, tile_ptr=None, n_tiles=0, tile_nodes=TILE_NODES):
-    """K1 v9: ``hops`` = [(in, add or None, out), ...] consecutive hops of one layer in ONE launch (see dc_spmm_chain);
-    every tile must be closed under the edges (``GraphCSR.tiles_closed``)."""
+def spmm_chain(rowptr, edges, self_w, hops, self_loop=False, tile_ptr=None, n_tiles=0, tile_nodes=TILE_NODES, max_tile_rows=0):
+    """K1 v9 / v10: ``hops`` = [(in, add or None, out), ...] consecutive hops of one layer in ONE launch; every tile must be
+    closed under the edges (``GraphCSR.tiles_closed``).  ``max_tile_rows`` > 0 selects the TMA-staged kernel
+    (dc_spmm_stage: tile slice in shared memory, any F % 4 == 0), else dc_spmm_chain (L1 gathers, F % 32 == 0)."""
     arr = (_abi.Hop * len(hops))()
     N, F = hops[0][0].shape
     nbytes = 0
@@ -540,8 +544,12 @@ def spmm_chain(rowptr, edges, self_w, hops, self_loop=False, tile_ptr=None, n_ti
                           _rows(out, "out"))
         nbytes += 8 * N * F + 4 * edges.shape[0] + 8 * N + 4 + (4 * N * F if add is not None else 0)
     e0 = _prof_begin()
-    _abi.call("dc_spmm_chain", _ptr(rowptr), _ptr(edges), _ptr(self_w), arr, len(hops), N, F, int(bool(self_loop)), _ptr(tile_ptr),
-              int(n_tiles), int(tile_nodes), _stream())
+    if max_tile_rows:
+        _abi.call("dc_spmm_stage", _ptr(rowptr), _ptr(edges), _ptr(self_w), arr, len(hops), N, F, int(bool(self_loop)),
+                  _ptr(tile_ptr), int(n_tiles), int(tile_nodes), int(max_tile_rows), _stream())
+    else:
+        _abi.call("dc_spmm_chain", _ptr(rowptr), _ptr(edges), _ptr(self_w), arr, len(hops), N, F, int(bool(self_loop)), _ptr(tile_ptr),
+                  int(n_tiles), int(tile_nodes), _stream())
     if e0 is not None:
         _prof_end(e0, op="spmm", F=F, N=N, E=edges.shape[0], bytes=nbytes, hops=len(hops))
     return [h[2] for h in hops]

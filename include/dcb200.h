@@ -121,6 +121,20 @@ typedef struct dc_hop {
 DC_API int dc_spmm_chain(const int32_t* rowptr, const void* edges, const float* self_w, const dc_hop_t* hops, int32_t num_hops,
                   int64_t num_nodes, int32_t F, int self_loop, const int32_t* tile_ptr, int64_t n_tiles, int32_t tile_nodes,
                   dc_stream_t stream);
+
+/* K1 v10 (TMA-staged hop chain): the contract of dc_spmm_chain, for any F % 4 == 0.  The (tile x feature slice) of each
+ * hop's input is copied into shared memory once by TMA (cp.async.bulk.tensor.2d over the strided [rows, slice] view,
+ * completion on an mbarrier) and the gathers are served from shared memory; the slice width adapts to the tile
+ * (4..8 float4 lanes per receiver so that max_tile_rows x lanes x 16 B fits 227 KB: 2000 rows -> 112-byte slices).
+ * Same rows, records, order and rounding as dc_spmm_lean / dc_spmm_chain: bit-identical.  REQUIRES closed tiles (whole
+ * graphs of a block-diagonal batch) like dc_spmm_chain; max_tile_rows = the largest tile (ignored without tile_ptr).
+ * dc_spmm_stage_supported() says whether tiles of that size fit (else DC_ENOSUP: use dc_spmm_chain).
+ * Replaces: the K consecutive MessagePassing.propagate calls of one PyG TAGConv forward / backward
+ * (models/model.py:71,77). */
+DC_API int dc_spmm_stage_supported(int64_t max_tile_rows, int32_t F);
+DC_API int dc_spmm_stage(const int32_t* rowptr, const void* edges, const float* self_w, const dc_hop_t* hops, int32_t num_hops,
+                         int64_t num_nodes, int32_t F, int self_loop, const int32_t* tile_ptr, int64_t n_tiles,
+                         int32_t tile_nodes, int64_t max_tile_rows, dc_stream_t stream);
 /* K1 v6 ("lean"): the same tile x 128-byte-slice mapping driven by packed 8-byte edge records
  * {int32 neighbour, fp32 weight} in CSR order (dc_pack_edges; w == NULL -> weight 1): one uniform 64-bit
  * load per edge instead of index/weight loads + shuffles, 8 row gathers in flight per lane, no predicates on

@@ -424,7 +424,7 @@ def test_hop_chain_rejects_bad_args(dc):
     ei = torch.randint(0, 100, (2, 500)).cuda()
     g = ops.GraphCSR(ei, 100, "tag", [0, 100])
     x = torch.randn(100, 24).cuda()
-    with pytest.raises(_abi.DcError):      # F % 32 != 0
+    with pytest.raises(_abi.DcError):      # F % 32 != 0 (the L1 chain kernel; dc_spmm_stage takes any F % 4 == 0)
         ops.spmm_chain(g.rowptr, g.edges, None, [(x, None, torch.empty_like(x))], tile_ptr=g.tile_ptr, n_tiles=g.n_tiles)
     x = torch.randn(100, 32).cuda()
     with pytest.raises(_abi.DcError):      # in aliases out
@@ -513,3 +513,58 @@ def test_grid_search_hands_unsplittable_clouds_to_brute_force(dc):
             assert ops.grid_took_it(out) == want_grid
     finally:
         ops.KNN_MODE = "auto"
+
+
+@pytest.mark.parametrize("F,graph_nodes", [(256, 2000), (256, 1500), (24, 2000), (28, 762), (64, 2900), (128, 3500), (36, 700)])
+def test_staged_hop_chain_bit_identical_to_single_hops(dc, F, graph_nodes):
+    """K1 v10 (dc_spmm_stage: tile slice staged in shared memory by TMA, 4..8 float4 lanes per receiver depending on the
+    tile size, any F % 4 == 0) == one generic launch per hop, bit for bit — forward chain into the strided [N, 3F] layout and
+    transposed chain with in-place addends; ragged batch with a deep row, isolated nodes, an empty and a one-node graph."""
+    from deformcontact_b200 import ops, _abi
+    sizes = [graph_nodes, 0, 1, graph_nodes // 2 + 3, 64]
+    ptr = [0]
+    for s_ in sizes:
+        ptr.append(ptr[-1] + s_)
+    N = ptr[-1]
+    gen = torch.Generator().manual_seed(F + graph_nodes)
+    eis = []
+    for lo, hi in zip(ptr[:-1], ptr[1:]):
+        n = hi - lo
+        if n == 0:
+            continue
+        e = torch.randint(0, n, (2, 9 * n), generator=gen)
+        e[1, : min(n, 200)] = 0          # one deep row (> 64 edges)
+        eis.append(e + lo)
+    ei = torch.cat(eis, 1).cuda()
+    g = ops.GraphCSR(ei, N, "tag", ptr)
+    assert g.tiles_closed and _abi.lib().dc_spmm_stage_supported(g._max_tile, F)
+    x = torch.randn(N, F, generator=gen).cuda()
+    buf = torch.zeros(N, 3 * F, device="cuda")
+    hs = [x] + [buf[:, i * F:(i + 1) * F] for i in range(3)]
+    ops.spmm_chain(g.rowptr, g.edges, None, [(hs[i], None, hs[i + 1]) for i in range(3)], tile_ptr=g.tile_ptr, n_tiles=g.n_tiles,
+                   max_tile_rows=g._max_tile)
+    ref = x
+    for i in range(3):
+        ref = ops.spmm(g.rowptr, g.nbr, ref, dis=g.dis)
+        assert torch.equal(hs[i + 1], ref), f"forward hop {i}"
+    adds = [torch.randn(N, F, generator=gen).cuda() for _ in range(3)]
+    d = [a.clone() for a in adds]
+    g3 = torch.randn(N, F, generator=gen).cuda()
+    ops.spmm_chain(g.t[0], g._edges_t, None, [(g3, d[2], d[2]), (d[2], d[1], d[1]), (d[1], d[0], d[0])], tile_ptr=g.tile_ptr,
+                   n_tiles=g.n_tiles, max_tile_rows=g._max_tile)
+    ref = g3
+    for i in (2, 1, 0):
+        ref = ops.spmm(g.t[0], g.t[1], ref, dis=g.dis, add=adds[i])
+        assert torch.equal(d[i], ref), f"transposed hop {i}"
+    # GCN weights (self loop term) through the same kernel
+    gg = ops.GraphCSR(ei, N, "gcn", ptr)
+    o = torch.empty_like(x)
+    ops.spmm_chain(gg.rowptr, gg.edges, gg.self_w, [(x, None, o)], self_loop=True, tile_ptr=gg.tile_ptr, n_tiles=gg.n_tiles,
+                   max_tile_rows=gg._max_tile)
+    assert torch.equal(o, ops.spmm(gg.rowptr, gg.nbr, x, dis=gg.dis, self_loop=True))
+
+
+def test_staged_hop_chain_unsupported_tile(dc):
+    from deformcontact_b200 import _abi
+    assert not _abi.lib().dc_spmm_stage_supported(5000, 256)     # 5000 rows x 64 B do not fit 227 KB
+    assert _abi.lib().dc_spmm_stage_supported(3500, 128)
