@@ -3,6 +3,7 @@ utils/pointcloud_utils.py:7-13, utils/pos_encoding.py:6-44).  All arithmetic is 
 import torch
 
 from . import ops
+from . import torch_ops  # noqa: F401  (registers torch.ops.dcb200.*)
 from .data import Data
 
 
@@ -24,27 +25,26 @@ def mesh_to_graph(vertices, triangles, encode=True, device="cuda"):
     return Data(x=x, edge_index=edge_index, pos=pos)
 
 
-def _with_order_hint(edge_index, tab, x, batch, ptr):
+def _with_order_hint(edge_index, order, x, batch, ptr):
     """One large cloud: remember the grid-cell order of its points for this edge_index, so the layers can run their hops
     on spatially coherent node labels (ops.REORDER; results unchanged).  The grid search hands the order over for free;
     after a brute-force search it is computed by dc_cell_order."""
     single = batch is None and (ptr is None or ptr.numel() == 2)
     if ops.REORDER and single and x.dim() == 2 and x.shape[1] == 3 and x.shape[0] >= ops.REORDER_MIN_NODES:
-        order = getattr(tab, "_cell_order", None)
-        ops.register_order_hint(edge_index, order if order is not None else ops.cell_order(x))
+        ops.register_order_hint(edge_index, order if order.numel() == x.shape[0] else ops.cell_order(x))
     return edge_index
 
 
 def knn_graph(x, k, batch=None, loop=False, ptr=None):
-    """torch_cluster.knn_graph(x, k, batch, loop, flow='source_to_target') -> int64 [2, E]."""
-    tab = ops.knn_table(x, k, batch=batch, ptr=ptr, loop=loop)
-    return _with_order_hint(ops.table_to_edge_index(tab), tab, x, batch, ptr)
+    """torch_cluster.knn_graph(x, k, batch, loop, flow='source_to_target') -> int64 [2, E] (``torch.ops.dcb200.knn_graph``)."""
+    edge_index, order = torch.ops.dcb200.knn_graph(x, int(k), batch, bool(loop), ptr)
+    return _with_order_hint(edge_index, order, x, batch, ptr)
 
 
 def radius_graph(x, r, batch=None, loop=False, max_num_neighbors=32, ptr=None):
-    """torch_cluster.radius_graph(x, r, batch, loop, max_num_neighbors) -> int64 [2, E]."""
-    tab, _ = ops.radius_table(x, r, batch=batch, ptr=ptr, loop=loop, max_num_neighbors=max_num_neighbors)
-    return _with_order_hint(ops.table_to_edge_index(tab), tab, x, batch, ptr)
+    """torch_cluster.radius_graph(x, r, batch, loop, max_num_neighbors) -> int64 [2, E] (``torch.ops.dcb200.radius_graph``)."""
+    edge_index, order = torch.ops.dcb200.radius_graph(x, float(r), batch, bool(loop), int(max_num_neighbors), ptr)
+    return _with_order_hint(edge_index, order, x, batch, ptr)
 
 
 def construct_graph(point_cloud, k=None, radius=None):

@@ -4,7 +4,8 @@ Mirrors models/model.py:23-97 (constructor arguments, module names — hence sta
 forward order) and models/model_loader.py:3-16.  The encoder loops (models/model.py:69-78) —
 the hot path — run in libdcb200 with bias+ReLU fused into the layer epilogue; the cross
 attention (models/model.py:7-21,82) runs on the same tcgen05 3xTF32 GEMMs
-(attention.py); the decoder MLP (:52-64,88) stays plain fp32 torch/cuBLAS.
+(attention.py), and so does the decoder MLP (:52-64,88; mlp.py, the concatenation of :84 passed as K-segments of
+its first GEMM).  ``DCB200_ATTENTION / DCB200_DECODER / DCB200_LOSS = torch`` select plain fp32 torch for comparison.
 
 ``attn_group``: the reference attention is unmasked over the whole batch (a soft node attends
 to the collider nodes of *every* sample, models/model.py:16-18).  ``attn_group=None``

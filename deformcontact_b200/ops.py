@@ -417,6 +417,18 @@ def graph_csr(edge_index, num_nodes, mode="tag", ptr_host=None, reorder=True):
     return g
 
 
+def adopt_csr(g):
+    """Put a structure that was built directly (``GraphCSR(...)``) into the cache under the key of the tensor it was built
+    from, so that the ``dcb200::`` custom ops — which take ``edge_index`` tensors — find it; returns that tensor."""
+    ei = g._src_edge_index
+    key = (ei.data_ptr(), tuple(ei.shape), ei._version, g.N, g.mode, ei.device.index, g.order is not None)
+    if _CSR_CACHE.get(key) is not g:
+        if len(_CSR_CACHE) >= _CSR_CACHE_MAX:
+            _CSR_CACHE.pop(next(iter(_CSR_CACHE)))
+        _CSR_CACHE[key] = g
+    return ei
+
+
 def clear_csr_cache():
     _CSR_CACHE.clear()
 

@@ -159,23 +159,31 @@ def test_graphnet_train_step_vs_oracle(dc, attn_group):
         assert_close_arbiter(po.grad, pr.grad, p64.grad, what=f"d{k}")
 
 
-@pytest.mark.parametrize("layer", ["TAGConv", "GCNConv"])
-def test_torch_custom_op_path_equals_autograd_function_path(dc, layer, monkeypatch):
-    """torch.ops.dcb200.* (registered custom ops + autograd) and the autograd.Function path run the same kernels."""
-    from deformcontact_b200 import layers as L
+@pytest.mark.parametrize("layer", ["TAGConv", "GCNConv", "GATConv", "MPNNLayer"])
+def test_layers_are_single_registered_custom_ops(dc, layer):
+    """Every layer dispatches through ONE registered ``torch.ops.dcb200.*`` op with a registered autograd formula (there is no
+    second autograd.Function implementation to drift), and a prebuilt ``ops.GraphCSR`` gives the same bits as the tensor."""
+    from deformcontact_b200 import layers as L, ops
+    assert not [n for n in dir(L) if n.endswith("Fn")], "layers.py must not carry its own autograd.Function bodies"
+    for op in ("tag_conv", "gcn_conv", "gat_conv", "mpnn_layer", "knn_graph", "radius_graph"):
+        assert op in dir(torch.ops.dcb200)
     x, ei = _graphs()["knn"]
-    _, ours = _pair(dc, layer, 21, 64)
-    res = {}
-    for flag in (True, False):
-        monkeypatch.setattr(L, "USE_TORCH_OPS", flag)
+    torch.manual_seed(3)
+    ours = getattr(dc, layer)(21 if layer != "MPNNLayer" else 24, 64).cuda()
+    if layer == "MPNNLayer":
+        x = torch.nn.functional.pad(x, (0, 3))
+    res = []
+    for prebuilt in (False, True):
         ours.zero_grad()
+        ops.clear_csr_cache()
         xo = x.clone().cuda().requires_grad_(True)
-        o = ours(xo, ei.cuda(), relu=True)
+        mode = {"TAGConv": "tag", "GCNConv": "gcn", "GATConv": "gat", "MPNNLayer": "plain"}[layer]
+        e = ops.GraphCSR(ei.cuda(), x.shape[0], mode) if prebuilt else ei.cuda()
+        o = ours(xo, e, relu=True)
         o.square().sum().backward()
-        res[flag] = [o.detach().clone(), xo.grad.clone()] + [p.grad.clone() for p in ours.parameters()]
-    for a, b in zip(res[True], res[False]):
-        assert torch.equal(a, b)
-    assert "tag_conv" in dir(torch.ops.dcb200) and "gcn_conv" in dir(torch.ops.dcb200)
+        res.append([o.detach().clone(), xo.grad.clone()] + [p.grad.clone() for p in ours.parameters()])
+    for a_, b_ in zip(*res):
+        assert torch.equal(a_, b_)
 
 
 def test_torch_ops_opcheck(dc):
@@ -187,6 +195,21 @@ def test_torch_ops_opcheck(dc):
                           test_utils=("test_schema", "test_faketensor"))
     torch.library.opcheck(torch.ops.dcb200.propagate.default, (x, ei, "tag", False, None, None, False, None),
                           test_utils=("test_schema", "test_faketensor"))
+    tu = ("test_schema", "test_faketensor")
+    w = torch.randn(16, 21, device="cuda", requires_grad=True)
+    att = [torch.randn(1, 1, 16, device="cuda", requires_grad=True) for _ in range(2)]
+    torch.library.opcheck(torch.ops.dcb200.gat_conv.default, (x, ei, w, att[0], att[1], b, 0.2, True, 0, None), test_utils=tu)
+    torch.library.opcheck(torch.ops.dcb200.gcn_conv.default, (x, ei, w, b, True, 0, None), test_utils=tu)
+    x24 = torch.randn(x.shape[0], 24, device="cuda")
+    mk = lambda *s_: torch.randn(*s_, device="cuda", requires_grad=True)
+    torch.library.opcheck(torch.ops.dcb200.mpnn_layer.default,
+                          (x24, ei, mk(16, 48), mk(16), mk(16, 16), mk(16), mk(16, 40), mk(16), mk(16, 16), mk(16), False, 0, None),
+                          test_utils=tu)
+    pos = torch.rand(500, 3, device="cuda")
+    torch.library.opcheck(torch.ops.dcb200.knn_graph.default, (pos, 6, None, False, None), test_utils=tu)
+    torch.library.opcheck(torch.ops.dcb200.radius_graph.default, (pos, 0.2, None, False, 32, None), test_utils=tu)
+    ei2, order = torch.ops.dcb200.knn_graph(pos, 6, None, False, None)
+    assert torch.equal(ei2, dc.knn_graph(pos, 6)) and order.numel() == 0
 
 
 @pytest.mark.parametrize("graph", ["knn", "mesh", "weird", "empty"])
