@@ -69,6 +69,7 @@ PROTOTYPES = {
     "dc_softmax_rows": (_int, [_p, _i64, _i64, _i64, _p]),
     "dc_softmax_bwd_rows": (_int, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "dc_relu_bwd": (_int, [_p, _p, _p, _i64, _p]),
+    "dc_relu_bwd_colsum": (_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _p, _p, _sz, _p]),
     "dc_knn": (_int, [_p, _p, _i64, _i64, _i32, _int, _p, _p]),
     "dc_radius": (_int, [_p, _p, _i64, _i64, _f32, _i32, _int, _p, _p, _p]),
     "dc_knn_grid_workspace_bytes": (_sz, [_i64]),

@@ -29,6 +29,34 @@ colsum_stage1(const float* __restrict__ X, int64_t ldx, int64_t M, int64_t N, fl
     partial[(int64_t)blockIdx.y * N + n] = t;
   }
 }
+// stage 1 of the fused ReLU backward + bias gradient: dX = dY * (Y > 0) written once, its column sums accumulated on the
+// way in exactly the order of colsum_stage1 (so dc_relu_bwd_colsum == dc_relu_bwd followed by dc_colsum, bit for bit)
+__global__ void __launch_bounds__(256)
+relu_bwd_colsum_stage1(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ dY, int64_t lddy, float* __restrict__ dX,
+                       int64_t lddx, int64_t M, int64_t N, float* __restrict__ partial) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t n = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS;
+  const int64_t r1 = min(M, r0 + CS_ROWS);
+  float s = 0.f;
+  if (n < N) {
+#pragma unroll 4
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const float g = Y[r * ldy + n] > 0.f ? dY[r * lddy + n] : 0.f;
+      dX[r * lddx + n] = g;
+      s += g;
+    }
+  }
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = sm[0][tx];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += sm[i][tx];
+    partial[(int64_t)blockIdx.y * N + n] = t;
+  }
+}
 __global__ void colsum_stage2(const float* __restrict__ partial, int64_t chunks, int64_t N, float* __restrict__ out) {
   int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (n >= N) return;
@@ -199,6 +227,24 @@ extern "C" int dc_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, floa
   dim3 grid((unsigned)cdiv(N, 32), (unsigned)chunks);
   colsum_stage1<<<grid, 256, 0, st>>>(X, ldx, M, N, static_cast<float*>(workspace));
   colsum_stage2<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(static_cast<float*>(workspace), chunks, N, out);
+  DC_LAUNCHED(2);
+  return DC_OK;
+}
+
+extern "C" int dc_relu_bwd_colsum(const float* Y, int64_t ldy, const float* dY, int64_t lddy, float* dX, int64_t lddx, int64_t M,
+                                  int64_t N, float* colsum, void* workspace, size_t workspace_bytes, dc_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DC_REQUIRE(M >= 0 && N >= 0, DC_EINVAL, "relu_bwd_colsum: negative size");
+  if (N == 0) return DC_OK;
+  DC_REQUIRE(colsum, DC_EINVAL, "relu_bwd_colsum: null colsum");
+  if (M == 0) { DC_CUDA(cudaMemsetAsync(colsum, 0, N * sizeof(float), st)); return DC_OK; }
+  DC_REQUIRE(Y && dY && dX && ldy >= N && lddy >= N && lddx >= N, DC_EINVAL, "relu_bwd_colsum: bad operands");
+  DC_REQUIRE(workspace && workspace_bytes >= dc_colsum_workspace_bytes(M, N), DC_EWORKSPACE, "relu_bwd_colsum: workspace");
+  int64_t chunks = cdiv(M, CS_ROWS);
+  DC_REQUIRE(chunks <= 65535, DC_ENOSUP, "relu_bwd_colsum: M too large");
+  dim3 grid((unsigned)cdiv(N, 32), (unsigned)chunks);
+  relu_bwd_colsum_stage1<<<grid, 256, 0, st>>>(Y, ldy, dY, lddy, dX, lddx, M, N, static_cast<float*>(workspace));
+  colsum_stage2<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(static_cast<float*>(workspace), chunks, N, colsum);
   DC_LAUNCHED(2);
   return DC_OK;
 }

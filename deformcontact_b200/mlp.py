@@ -33,9 +33,7 @@ class _LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         weight, y, *segs = ctx.saved_tensors
-        dy = dy.contiguous()
-        if ctx.relu:
-            dy = ops.relu_bwd(y, dy)
+        dy, db = ops.relu_bwd_db(y, dy.contiguous(), ctx.relu, ctx.has_bias)   # ReLU backward + bias gradient in one pass
         M, N = dy.shape
         dW = torch.empty_like(weight)
         dsegs = []
@@ -44,7 +42,6 @@ class _LinearFn(torch.autograd.Function):
             Ws = weight[:, o:o + k]
             dsegs.append(ops.gemm([(dy, Ws)], M, k, trans_b=False) if need else None)          # dY W_s
             ops.gemm([(dy, s)], N, k, trans_a=True, trans_b=False, out=dW[:, o:o + k])          # dY^T X_s
-        db = ops.colsum(dy) if ctx.has_bias else None
         return (dW, db, None, *dsegs)
 
 

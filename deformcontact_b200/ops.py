@@ -707,6 +707,28 @@ def relu_bwd(Y, dY):
     return dX
 
 
+def relu_bwd_colsum(Y, dY):
+    """(dX, colsum(dX)) with dX = dY * (Y > 0) in one pass; see dc_relu_bwd_colsum."""
+    _need(Y, _f32, "Y"), _need(dY, _f32, "dY")
+    M, N = Y.shape
+    ldy, lddy = _rows(Y, "Y"), _rows(dY, "dY")
+    dX = torch.empty((M, N), dtype=_f32, device=Y.device)
+    out = torch.empty(N, dtype=_f32, device=Y.device)
+    nb = _abi.lib().dc_colsum_workspace_bytes(M, N)
+    ws = _workspace(nb, Y.device)
+    _abi.call("dc_relu_bwd_colsum", _ptr(Y), ldy, _ptr(dY), lddy, _ptr(dX), N, M, N, _ptr(out), _ptr(ws), nb, _stream())
+    return dX, out
+
+
+def relu_bwd_db(Y, dY, relu, need_db):
+    """The head of every layer backward: undo the fused ReLU and take the bias gradient -> (dY', db or None)."""
+    if relu and need_db:
+        return relu_bwd_colsum(Y, dY)
+    if relu:
+        dY = relu_bwd(Y, dY)
+    return dY, (colsum(dY) if need_db else None)
+
+
 # ----------------------------------------------------------------------------- K4
 def _ptr_tensor(num_points, batch, ptr, device):
     if ptr is not None:

@@ -113,9 +113,7 @@ def tag_conv_backward(dout: Tensor, out: Tensor, x: Tensor, hops: Tensor, edge_i
                       need_dw: bool) -> Tuple[Tensor, Tensor, Tensor]:
     """-> (dx, dbias, dW stacked [K+1, Fo, Fi]); empty tensors for gradients that are not needed."""
     g = _csr(edge_index, x.shape[0], "tag" if normalize else "plain", ptr)
-    dout = dout.contiguous()
-    if relu:
-        dout = ops.relu_bwd(out, dout)
+    dout, db = ops.relu_bwd_db(out, dout.contiguous(), relu, need_db)   # ReLU backward + bias gradient in one pass
     dout = g.to_internal(dout)      # the saved hops are in the structure's node order
     N, Fo = dout.shape
     Fi = x.shape[1]
@@ -127,7 +125,7 @@ def tag_conv_backward(dout: Tensor, out: Tensor, x: Tensor, hops: Tensor, edge_i
             ops.gemm([(dout, h)], Fo, Fi, True, False, out=dws[k], precision=precision)
     else:
         dws = dout.new_empty(0)
-    db = ops.colsum(dout) if need_db else dout.new_empty(0)
+    db = db if need_db else dout.new_empty(0)
     if need_dx:
         gk = ops.gemm([(dout, weights[K])], N, Fi, False, False, precision=precision)
         if ops.K1_CHAIN >= 2 and K > 0:
@@ -195,12 +193,10 @@ def _(x, edge_index, weight, bias, relu, precision, ptr):
 def gcn_conv_backward(dout: Tensor, out: Tensor, x: Tensor, edge_index: Tensor, weight: Tensor, relu: bool, precision: int,
                       ptr: Optional[List[int]], need_dx: bool, need_db: bool) -> Tuple[Tensor, Tensor, Tensor]:
     g = _csr(edge_index, x.shape[0], "gcn", ptr)
-    dout = dout.contiguous()
-    if relu:
-        dout = ops.relu_bwd(out, dout)
+    dout, db = ops.relu_bwd_db(out, dout.contiguous(), relu, need_db)
     N, Fo = dout.shape
     Fi = x.shape[1]
-    db = ops.colsum(dout) if need_db else dout.new_empty(0)
+    db = db if need_db else dout.new_empty(0)
     dxw = g.propagate(dout, transpose=True)
     dx = ops.gemm([(dxw, weight)], N, Fi, False, False, precision=precision) if need_dx else dout.new_empty(0)
     dw = ops.gemm([(dxw, x.contiguous())], Fo, Fi, True, False, precision=precision)
@@ -262,13 +258,11 @@ def gat_conv_backward(dout: Tensor, out: Tensor, x: Tensor, edge_index: Tensor, 
                       need_db: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """-> (dx, dW, datt_src, datt_dst, dbias); empty tensors for gradients that are not needed."""
     g = _csr(edge_index, x.shape[0], "gat", ptr)
-    dout = dout.contiguous()
-    if relu:
-        dout = ops.relu_bwd(out, dout)
+    dout, db = ops.relu_bwd_db(out, dout.contiguous(), relu, need_db)
     N, C_ = dout.shape
     Fi = x.shape[1]
     x = x.contiguous()
-    db = ops.colsum(dout) if need_db else dout.new_empty(0)
+    db = db if need_db else dout.new_empty(0)
     rpt, nbt, eidt = g.t
     # through the aggregation: dxs[j] = sum_{e: src=j} alpha_e dout[dst_e] + alpha_self[j] dout[j]
     dz_e, dz_s, da_dst = ops.gat_bwd_edge(g, a_src, a_dst, negative_slope, alpha_e, alpha_s, xs, dout)

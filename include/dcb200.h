@@ -264,6 +264,12 @@ DC_API int dc_edge_loss(const int32_t* rowptr, const int32_t* nbr, const int32_t
 
 /* dX = dY * (Y > 0)  (backward of the ReLU fused into dc_gemm's epilogue; models/model.py:71,77) */
 DC_API int dc_relu_bwd(const float* Y, const float* dY, float* dX, int64_t numel, dc_stream_t stream);
+/* The same with the bias gradient taken on the way: dX = dY * (Y > 0) and colsum[n] = sum_m dX[m, n] in one pass over
+ * [M, N] matrices (leading dimensions ld*), summed in the order of dc_colsum (bit-identical to dc_relu_bwd + dc_colsum);
+ * workspace >= dc_colsum_workspace_bytes(M, N).  Replaces relu'() followed by bias.grad of every Linear / conv + ReLU pair
+ * in the backward of models/model.py:71,77,88. */
+DC_API int dc_relu_bwd_colsum(const float* Y, int64_t ldy, const float* dY, int64_t lddy, float* dX, int64_t lddx, int64_t M,
+                              int64_t N, float* colsum, void* workspace, size_t workspace_bytes, dc_stream_t stream);
 
 /* ---------------------------------------------------------------- K4: kNN / radius graph
  * Replaces torch_cluster.knn_graph / radius_graph as called at utils/pointcloud_utils.py:10,12

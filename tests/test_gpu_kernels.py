@@ -568,3 +568,17 @@ def test_staged_hop_chain_unsupported_tile(dc):
     from deformcontact_b200 import _abi
     assert not _abi.lib().dc_spmm_stage_supported(5000, 256)     # 5000 rows x 64 B do not fit 227 KB
     assert _abi.lib().dc_spmm_stage_supported(3500, 128)
+
+
+@pytest.mark.parametrize("M,N", [(1, 1), (5000, 256), (2049, 3), (777, 100)])
+def test_relu_bwd_colsum_equals_the_two_kernels(dc, M, N):
+    """dc_relu_bwd_colsum == dc_relu_bwd followed by dc_colsum, bit for bit (same summation order)."""
+    from deformcontact_b200 import ops
+    g = torch.Generator().manual_seed(M + N)
+    Y = torch.randn(M, N, generator=g).cuda().relu()
+    dY = torch.randn(M, N, generator=g).cuda()
+    dX, cs = ops.relu_bwd_colsum(Y, dY)
+    ref = ops.relu_bwd(Y, dY)
+    assert torch.equal(dX, ref) and torch.equal(dX, dY * (Y > 0))
+    assert torch.equal(cs, ops.colsum(ref))
+    assert_close(cs, ref.double().sum(0).float(), what="colsum")
