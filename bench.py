@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--layer", default="tag", choices=["tag", "gcn", "gat", "mpnn"], help="C5: which layer")
     ap.add_argument("--no-tiles", action="store_true", help="C5: fixed 2048-node tiles instead of graph-aligned tiles")
     ap.add_argument("--hidden", type=int, default=256, help="C5 sweep: feature width")
+    ap.add_argument("--order", default="random", choices=["random", "morton"],
+                    help="C5: node order inside each graph: as generated (spatially random: worst-case gather locality) or Morton-sorted")
     ap.add_argument("--edges", type=float, default=10e6, help="C5 sweep: number of edges")
     return ap.parse_args()
 
@@ -485,6 +487,16 @@ def run_layer(args, emit=True):
     N = B * n
     g = torch.Generator(device=dev).manual_seed(0)
     pos = torch.rand(N, 3, generator=g, device=dev) - 0.5
+    if getattr(args, "order", "random") == "morton":     # mesh-like locality: nodes of every graph in Z-curve order
+        q = ((pos + 0.5) * 1023).long().clamp_(0, 1023)
+        def spread(v):
+            v = (v | (v << 16)) & 0x030000FF
+            v = (v | (v << 8)) & 0x0300F00F
+            v = (v | (v << 4)) & 0x030C30C3
+            return (v | (v << 2)) & 0x09249249
+        code = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+        code = code + (torch.arange(N, device=dev) // n) * (1 << 30)
+        pos = pos[torch.argsort(code)]
     ptr = torch.arange(B + 1, device=dev) * n
     ei = dc.knn_graph(pos, k, ptr=ptr)
     E = ei.shape[1]
@@ -538,6 +550,7 @@ def run_layer(args, emit=True):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": fb_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": f"C5 {type(layer).__name__}({F},{F}) layer fwd+bwd, {B} kNN-{k} graphs x {n} nodes, N={N}, E={E}",
+                       "node_order": getattr(args, "order", "random"),
                        "l2": f"hop working set {hop_bytes / 1e6:.0f} MB vs 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": int(launches),
             "fwd_ms": fwd_ms, "fwd_edges_per_sec": E / (fwd_ms * 1e-3),

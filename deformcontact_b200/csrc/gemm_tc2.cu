@@ -101,6 +101,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tensormap_acquire(const CUtensorMap* map) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(map) : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t"
@@ -243,10 +246,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     if (lane == 0) {
       const CUtensorMap* mA[4] = {&mapA0, &mapA1, &mapA2, &mapA3};
       const CUtensorMap* mB[4] = {&mapB0, &mapB1, &mapB2, &mapB3};
-      int it = 0, pidx = 0;
+      int it = 0, pidx = 0, fenced = -1;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
         const T2Item item = t2_item(p, w, pidx);
-        if (p.batch) { mA[0] = item.mapA; mB[0] = item.mapB; }
+        if (p.batch) {
+          mA[0] = item.mapA; mB[0] = item.mapB;
+          if (fenced != pidx) {
+            // Tensor maps that live in GLOBAL memory (the uploaded problem table; its workspace address is recycled from
+            // launch to launch) must be acquired through the tensormap proxy before the TMA unit may use them, or it can
+            // serve a stale descriptor cached under the same address (CUDA programming guide, tensor maps in global memory).
+            tensormap_acquire(item.mapA);
+            tensormap_acquire(item.mapB);
+            fenced = pidx;
+          }
+        }
         int seg = 0, seg_kb0 = 0;   // segment containing k-block kb, and its first k-block
         for (int kb = item.kb0; kb < item.kb1; ++kb, ++it) {
           if (!p.batch)
@@ -332,8 +345,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           uint4* src = (i & 1) ? b : a;
           const int idx = t + (i >> 1) * 128;
           const uint4 v = src[idx];
-          const uint4 h = make_uint4(v.x & 0xFFFFE000u, v.y & 0xFFFFE000u, v.z & 0xFFFFE000u, v.w & 0xFFFFE000u);
-          // lo = RN_tf32(x - trunc_tf32(x)): the tensor core TRUNCATES a tf32 operand to its upper 19 bits, so an unrounded
+          // raw_hi: the MMA reads the raw fp32 tile as hi, i.e. hi = trunc_tf32(x) (the tensor core ignores the low 13 bits);
+          // else hi = RN_tf32(x) is written back over the tile: |lo| halves and the dropped lo*lo term loses its sign bias
+          const uint4 h = p.raw_hi ? make_uint4(v.x & 0xFFFFE000u, v.y & 0xFFFFE000u, v.z & 0xFFFFE000u, v.w & 0xFFFFE000u)
+                                   : make_uint4(rn_tf32(__uint_as_float(v.x)), rn_tf32(__uint_as_float(v.y)),
+                                                rn_tf32(__uint_as_float(v.z)), rn_tf32(__uint_as_float(v.w)));
+          // lo = RN_tf32(x - hi): the tensor core TRUNCATES a tf32 operand to its upper 19 bits, so an unrounded
           // remainder would lose up to 2^-10 of itself, always towards zero — a systematic shrink of both cross terms
           // (2 x 2^-22 relative on average, the larger part of the 0.8-1.2e-6 error measured in round 1).  Rounded to
           // nearest here, the remainder's error is unbiased and the truncation finds only zeros to drop.
@@ -659,6 +676,7 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
   p.drain_kb = T2_DRAIN_KB;
   p.relu = relu; p.accumulate = accumulate;
   p.raw_hi = 1;
+  if (const char* e = getenv("DCB200_T2_RAWHI")) p.raw_hi = e[0] == '1';
   static DeviceOnce attr_set;
   if (attr_set.first()) {
     DC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));

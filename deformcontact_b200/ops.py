@@ -169,15 +169,19 @@ def _device_table(key, build, device):
     return t
 
 
-def make_tiles(ptr_host, num_nodes, target=TILE_NODES):
-    """Tile boundaries for dc_spmm_tiled: whole graphs of the block-diagonal batch, small graphs
-    merged up to ~target receivers, large graphs split into target-sized chunks."""
+TILE_WHOLE_MAX = 3600     # largest graph kept as ONE tile: what dc_spmm_stage can hold in shared memory (4 float4 lanes)
+
+
+def make_tiles(ptr_host, num_nodes, target=TILE_NODES, whole_max=TILE_WHOLE_MAX):
+    """Tile boundaries for the K1 kernels: whole graphs of the block-diagonal batch (a tile that is a union of whole graphs is
+    closed under the edges, which the hop-chain kernels need), small graphs merged up to ~target receivers, graphs of more than
+    ``whole_max`` rows split into target-sized chunks (those tiles are not closed: one launch per hop, L1 gathers)."""
     if ptr_host is None:
         return None
     tiles, cur = [0], 0
     for lo, hi in zip(ptr_host[:-1], ptr_host[1:]):
         n = hi - lo
-        if n > target + target // 4:
+        if n > max(target + target // 4, whole_max):
             if cur != lo:
                 tiles.append(lo)
             k = -(-n // target)
@@ -189,6 +193,9 @@ def make_tiles(ptr_host, num_nodes, target=TILE_NODES):
             if hi - cur > target + target // 4 and cur != lo:
                 tiles.append(lo)
                 cur = lo
+            if n > target + target // 4:      # a large graph that still fits: a tile of its own
+                tiles.append(hi)
+                cur = hi
         # else: keep merging
     if tiles[-1] != num_nodes:
         tiles.append(num_nodes)
@@ -600,11 +607,17 @@ def edge_relu(rowptr, nbr, p, q, r=None, mode=0):
 
 
 # ----------------------------------------------------------------------------- K2 / K3
+# accuracy lab (scripts/acc_lab.py): DCB200_GEMM=fp32 forces the exact-fp32 FFMA kernel for every product
+FORCE_GEMM_PRECISION = {"fp32": GEMM_FP32, "tc": GEMM_PREFER_TC}.get(os.environ.get("DCB200_GEMM", ""))
+
+
 def gemm(segs, M, N, trans_a=False, trans_b=True, bias=None, relu=False, out=None, accumulate=False,
          precision=GEMM_AUTO):
     """C[M,N] = act(sum_s opA(A_s) opB(B_s) + bias) (+C); segs = [(A_s, B_s), ...]; see dc_gemm.
     More than ``_abi.MAX_SEGS`` segments (a decoder fed by >= 4 attention heads, TAGConv with K >= 4) are chained
     in groups with ``accumulate``; bias and ReLU are applied by the last group."""
+    if FORCE_GEMM_PRECISION is not None:
+        precision = FORCE_GEMM_PRECISION
     if len(segs) > _abi.MAX_SEGS:
         groups = [segs[i:i + _abi.MAX_SEGS] for i in range(0, len(segs), _abi.MAX_SEGS)]
         for gi, grp in enumerate(groups):
@@ -663,7 +676,7 @@ def gemm_batched(problems, trans_a=False, trans_b=True, relu=False, accumulate=F
         arr[i] = _abi.GemmProblem(A.data_ptr(), lda, B.data_ptr(), ldb, Cm.data_ptr(), ldc, M, N, K, _ptr(E),
                                   _rows(E, "E") if E is not None else 0, _ptr(rowv))
         flops += 2.0 * M * N * K
-    if not ok:
+    if not ok or FORCE_GEMM_PRECISION == GEMM_FP32:
         for q in problems:
             A, B, Cm = q[:3]
             gemm([(A, B)], Cm.shape[0], Cm.shape[1], trans_a=trans_a, trans_b=trans_b, relu=relu, out=Cm, accumulate=accumulate)

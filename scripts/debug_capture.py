@@ -10,6 +10,7 @@ rest, rigid, deformed = synthetic.make_batch(4, 300, 8)
 torch.manual_seed(0)
 model = dc.load_model(hidden_dim=64, attn_group=2).cuda()
 x = torch.randn(1200, 64, device="cuda")
+OPT = torch.optim.Adam(model.parameters(), lr=4e-4, capturable=True)
 keep = []
 
 
@@ -27,6 +28,22 @@ def body():
             return conv(x, rest.edge_index, relu=True, ptr=rest._ptr_host).sum()
     if stage == "gemm":
         return ops.gemm([(x, model.conv_layers_resting[1].lins[0].weight)], 1200, 64).sum()
+    if stage == "gemmb":      # one batched launch (host-built problem table staged through pinned memory)
+        A = [x[i * 300:(i + 1) * 300] for i in range(3)]
+        outs = [torch.empty(300, 300, device="cuda") for _ in range(3)]
+        ops.gemm_batched([(a, a, o) for a, o in zip(A, outs)], trans_b=True)
+        return sum(o.sum() for o in outs)
+    if stage == "attn":
+        from deformcontact_b200 import attention
+        xs, xr = x, x[:600] * 0.5
+        with torch.no_grad():
+            o = attention.cross_attention(xs, xr, model.multihead_attention.attention_heads, [0, 600, 1200], [0, 300, 600], 1)
+        return o.sum()
+    if stage == "adam":
+        for p in model.parameters():
+            p.grad = torch.ones_like(p) * 1e-3
+        OPT.step()
+        return sum(p.sum() for p in model.parameters())
     if stage == "encode":
         with torch.no_grad():
             a, b = model.encode(rest, rigid)

@@ -1,4 +1,4 @@
-"""K1 v9 lab: the three hops of a TAGConv layer as one chain launch vs three launches, forward (lean) and
+"""K1 v9 / v10 lab (v10 = dc_spmm_stage, tile slice staged in shared memory by TMA): the three hops of a TAGConv layer as one chain launch vs three launches, forward (lean) and
 transposed-with-addend (blocks / lean), bit-equality against the per-hop kernels, C5 graph.
 usage: python scripts/k1_chain_lab.py [--nodes 2000] [--graphs 256] [--k 8] [--F 256] [--out file.json]"""
 import argparse, json, os, sys
@@ -53,11 +53,19 @@ def fwd_sep(b):
     v = views(b); src = x
     for i in range(3):
         ops.spmm_lean(G.rowptr, G.edges, None, src, out=v[i], tile_ptr=G.tile_ptr, n_tiles=G.n_tiles); src = v[i]
-def fwd_chain(b):
+def fwd_chain(b, staged=False):
     v = views(b)
-    ops.spmm_chain(G.rowptr, G.edges, None, [(x, None, v[0]), (v[0], None, v[1]), (v[1], None, v[2])], tile_ptr=G.tile_ptr, n_tiles=G.n_tiles)
+    ops.spmm_chain(G.rowptr, G.edges, None, [(x, None, v[0]), (v[0], None, v[1]), (v[1], None, v[2])], tile_ptr=G.tile_ptr, n_tiles=G.n_tiles,
+                   max_tile_rows=G._max_tile if staged else 0)
 fwd_sep(buf_a); buf_b.zero_(); fwd_chain(buf_b)
 ok = torch.equal(buf_a, buf_b)
+buf_c = torch.zeros(N, 3 * F, device=dev)
+fwd_chain(buf_c, True)
+ok_staged = torch.equal(buf_a, buf_c)
+ms = ev_time(lambda: fwd_chain(buf_c, True), a.reps)
+res["fwd_chain_staged_v10"] = {"ms": round(ms, 4), "ms_per_hop": round(ms / 3, 4), "frac": round(3 * hop_bytes / (ms * 1e-3) / 1e9 / peak, 3), "bit_equal": ok_staged}
+print("fwd_chain_staged_v10", json.dumps(res["fwd_chain_staged_v10"]), flush=True)
+del buf_c
 for name, fn in (("fwd_3_launches", lambda: fwd_sep(buf_a)), ("fwd_chain", lambda: fwd_chain(buf_b))):
     ms = ev_time(fn, a.reps)
     res[name] = {"ms": round(ms, 4), "ms_per_hop": round(ms / 3, 4), "frac": round(3 * hop_bytes / (ms * 1e-3) / 1e9 / peak, 3), "bit_equal": ok}
@@ -80,14 +88,15 @@ def bwd_sep(variant):
         for i in (2, 1, 0):
             s = G.propagate(s, transpose=True, add=d[i], out=d[i])
     return d, run
-def bwd_chain():
+def bwd_chain(staged=False):
     d = [t.clone() for t in adds]
     def run():
-        ops.spmm_chain(G.t[0], G._edges_t, None, [(g3, d[2], d[2]), (d[2], d[1], d[1]), (d[1], d[0], d[0])], tile_ptr=G.tile_ptr, n_tiles=G.n_tiles)
+        ops.spmm_chain(G.t[0], G._edges_t, None, [(g3, d[2], d[2]), (d[2], d[1], d[1]), (d[1], d[0], d[0])], tile_ptr=G.tile_ptr, n_tiles=G.n_tiles,
+                       max_tile_rows=G._max_tile if staged else 0)
     return d, run
 outs = {}
-for name, (d, run) in (("T_3_blocks", bwd_sep("blocks")), ("T_3_lean", bwd_sep("lean")), ("T_chain", bwd_chain())):
-    if name != "T_chain":
+for name, (d, run) in (("T_3_blocks", bwd_sep("blocks")), ("T_3_lean", bwd_sep("lean")), ("T_chain", bwd_chain()), ("T_chain_staged_v10", bwd_chain(True))):
+    if not name.startswith("T_chain"):
         ops.K1_VARIANT = name.split("_")[-1]
     run(); torch.cuda.synchronize()
     outs[name] = [t.clone() for t in d]
@@ -95,7 +104,8 @@ for name, (d, run) in (("T_3_blocks", bwd_sep("blocks")), ("T_3_lean", bwd_sep("
     res[name] = {"ms": round(ms, 4), "ms_per_hop": round(ms / 3, 4), "frac": round(3 * hb / (ms * 1e-3) / 1e9 / peak, 3)}
     print(name, json.dumps(res[name]), flush=True)
 ops.K1_VARIANT = "auto"
-eq = all(torch.equal(p, q) for p, q in zip(outs["T_3_blocks"], outs["T_chain"])) and all(torch.equal(p, q) for p, q in zip(outs["T_3_lean"], outs["T_chain"]))
+eq = (all(torch.equal(p, q) for p, q in zip(outs["T_3_blocks"], outs["T_chain"])) and all(torch.equal(p, q) for p, q in zip(outs["T_3_lean"], outs["T_chain"]))
+      and all(torch.equal(p, q) for p, q in zip(outs["T_chain_staged_v10"], outs["T_chain"])))
 res["T_bit_equal"] = eq
 print("T_bit_equal", eq)
 if a.out:
