@@ -153,6 +153,46 @@ def oracle_train_arm(args, steps, warmup):
                       f"os.cpu_count={os.cpu_count()}"}, mean
 
 
+def oracle_gpu_arm(args, rest, rigid, deformed, n_graphs):
+    """What the reference's own formulation costs on THIS GPU: the oracle port (index_select -> mul -> scatter_add_ hops,
+    nn.Linear / torch.mm on cuBLAS, F.softmax, autograd, Adam) run on the device-resident batch with stock PyTorch CUDA kernels —
+    none of libdcb200 on that path.  fp32 (TF32 off: the precision class of our path) and with TF32 allowed (does not meet the
+    1e-5 bar; for context).  A reported baseline, like the CPU figure; upstream train.py would run this way on a GPU box."""
+    import oracle
+    out = {}
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.manual_seed(0)
+        model = oracle.load_model(attn_group=args.attn_group).to(rest.x.device)
+        opt = torch.optim.Adam(model.parameters(), lr=4e-4)
+
+        def step():
+            opt.zero_grad()
+            loss, _, _ = oracle.train_step_loss(model, rest, rigid, deformed)
+            loss.backward()
+            opt.step()
+        try:
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            out["tf32" if tf32 else "fp32"] = {"value": n_graphs / (ms * 1e-3), "unit": "graphs/s", "ms_per_step": ms}
+        except Exception as e:   # e.g. out of memory for the [E, F] temporaries: report, never fail the line
+            out["tf32" if tf32 else "fp32"] = {"error": repr(e)[:200]}
+        del model, opt
+        torch.cuda.empty_cache()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out["kind"] = ("oracle port on the same GPU, stock PyTorch CUDA kernels (index_select / scatter_add_ atomics / cuBLAS / softmax), "
+                   f"{n_graphs} graphs per step, 3 steps after 2 warm-up, CUDA events")
+    return out
+
+
 def config_dict(args, world):
     if args.scaling == "strong":
         btot, per = args.global_batch, -(-args.global_batch // world)
@@ -433,9 +473,10 @@ def run_ours(args):
         runner = None
         gc.collect(); torch.cuda.empty_cache()
 
-    cpu_baseline = None
+    cpu_baseline = torch_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline, _ = oracle_train_arm(args, 20, 3)
+        torch_gpu = oracle_gpu_arm(args, rest, rigid, deformed, Bg)
 
     subs = {}
     if rank == 0 and world == 1 and args.all_configs:
@@ -466,7 +507,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": cfg,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
                 "gpu_launches_per_step": int(launches_per_step), "roofline": roofline, "roofline_k1": roofline_k1,
-                "cpu_baseline": cpu_baseline, **extra}
+                "cpu_baseline": cpu_baseline, "torch_gpu_baseline": torch_gpu, **extra}
         if dp_err is not None:
             line["dp_grad_rel_err"] = dp_err
         line.update(subs)

@@ -39,7 +39,9 @@ constexpr int T2_STAGE_BYTES = 4 * T2_TILE_BYTES;             // A hi(raw), A lo
 constexpr int T2_EPI_ROW = 20;                                // staging row: 16 floats + 4 pad
 constexpr int T2_EPI_WARP_FLOATS = 32 * T2_EPI_ROW;
 constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOATS * 4 + 256 + 1024;
-constexpr int T2_DRAIN_KB = 8;                                // chain length in k-blocks (32 MMA steps)
+constexpr int T2_DRAIN_KB = 4;                                // chain length in k-blocks (16 main MMA steps), long contractions
+constexpr int T2_DRAIN_KB_SHORT = 1;                          // ... short contractions (kb_total <= T2_SHORT_KB)
+constexpr int T2_SHORT_KB = 16;                               // K <= 512
 constexpr int T2_MAX_KPARTS = 64;   // weight gradients: 256 x 256 outputs over 512k nodes need ~37 parts to fill 148 SMs
 
 // one problem of a batched launch (device table; the tensor maps are read by TMA straight from global memory)
@@ -512,6 +514,21 @@ int make_map2(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t rows,
   return DC_OK;
 }
 
+// Chain length in k-blocks.  The tensor core rounds its fp32 accumulator towards zero on every MMA, a bias of ~0.5 ulp per
+// MMA on the main (hi x hi) chain: 32 MMAs per chain gave 0.8-1.0e-6 against fp64 (round 1), 16 give 4.6e-7, 4 give ~3e-7
+// (profiles/r02_gemm_drain_lab.txt).  Short contractions (K <= 512: the attention scores Q K^T and dP = dO Xr^T, whose
+// ABSOLUTE error the unscaled softmax and its backward amplify) drain every k-block; long ones every T2_DRAIN_KB.
+int t2_drain_kb(int64_t kb_total) {
+  static int d_long = -1, d_short = -1;
+  if (d_long < 0) {
+    const char* e = getenv("DCB200_DRAIN_KB");
+    d_long = (e && atoi(e) > 0) ? atoi(e) : T2_DRAIN_KB;
+    const char* es = getenv("DCB200_DRAIN_KB_SHORT");
+    d_short = (es && atoi(es) > 0) ? atoi(es) : T2_DRAIN_KB_SHORT;
+  }
+  return kb_total <= T2_SHORT_KB ? (d_short < d_long ? d_short : d_long) : d_long;
+}
+
 int t2_k_parts(int64_t M, int64_t N, int64_t kb_total) {
   const int64_t mn = cdiv(M, T2_BM) * cdiv(N, T2_BN);
   if (mn >= sm_count()) return 1;
@@ -572,8 +589,7 @@ int gemm_tc2(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t 
   p.kb_per_part = (int)(cdiv(cdiv(p.kb_total, p.k_parts), T2_DRAIN_KB) * T2_DRAIN_KB);   // whole chains per part
   p.k_parts = (int)cdiv(p.kb_total, p.kb_per_part);
   p.items = p.m_tiles * p.n_chunks * p.k_parts;
-  p.drain_kb = T2_DRAIN_KB;
-  if (const char* e = getenv("DCB200_DRAIN_KB")) p.drain_kb = atoi(e) > 0 ? atoi(e) : T2_DRAIN_KB;
+  p.drain_kb = t2_drain_kb(p.kb_total);
   p.C = C; p.ldc = ldc; p.bias = bias; p.relu = relu; p.accumulate = accumulate;
   // measured r01: identical error against fp64 with and without the masked copy (the tensor core reads only the
   // upper 19 bits of a tf32 operand), 7-10 % faster without the extra shared-memory write
@@ -630,6 +646,7 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
   T2Problem* tab = reinterpret_cast<T2Problem*>(hbase);
   int* item_off = reinterpret_cast<int*>(hbase + tab_bytes);
   int64_t items = 0;
+  int64_t max_kb = 0;
   for (int i = 0; i < count; ++i) {
     const dc_gemm_problem& q = probs[i];
     DC_REQUIRE(q.M >= 0 && q.N >= 0 && q.K >= 0, DC_EINVAL, "gemm_batched: negative size in problem %d", i);
@@ -655,6 +672,7 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
     t.E = q.E; t.rowv = q.rowv; t.lde = q.lde;
     DC_REQUIRE(!q.E || (q.rowv && q.lde >= q.N), DC_EINVAL, "gemm_batched: problem %d: epilogue operand needs rowv and lde >= N", i);
     t.kb_total = (int)cdiv(q.K, T2_BK);
+    if (t.kb_total > max_kb) max_kb = t.kb_total;
     t.n_chunks = (int)cdiv(q.N, T2_BN);
     items += cdiv(q.M, T2_BM) * t.n_chunks;
     DC_REQUIRE(items < (1ll << 30), DC_ENOSUP, "gemm_batched: too many work items");
@@ -673,7 +691,7 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
   p.b_mn = transB ? 0 : 1;
   p.k_parts = 1;
   p.items = (int)items;
-  p.drain_kb = T2_DRAIN_KB;
+  p.drain_kb = t2_drain_kb(max_kb);
   p.relu = relu; p.accumulate = accumulate;
   p.raw_hi = 1;
   if (const char* e = getenv("DCB200_T2_RAWHI")) p.raw_hi = e[0] == '1';

@@ -142,8 +142,10 @@ K1_VARIANT = os.environ.get("DCB200_K1", "auto")
 K1_FLAGS = int(os.environ.get("DCB200_K1_FLAGS", "28"))
 # hop chain (K1 v9): 0 = one launch per hop; 1 = chain the forward hops of a layer; 2 = forward and backward chains
 K1_CHAIN = int(os.environ.get("DCB200_K1_CHAIN", "2"))
-# K1 v10: hop chains with the tile slice staged in shared memory by TMA (dc_spmm_stage) where the tile fits; 0 = v9 chain
-K1_STAGE = int(os.environ.get("DCB200_K1_STAGE", "1"))
+# K1 v10: hop chains with the tile slice staged in shared memory by TMA (dc_spmm_stage) where the tile fits; 0 = v9 chain.
+# Measured r02 (C5, F=256, 2000-node graphs): 0.519 ms per forward hop against 0.348 for the L1 chain (the load and gather phases
+# of the one resident CTA do not overlap, and a 227 KB carve-out leaves ~28 KB of L1 for the edge records) -> off by default.
+K1_STAGE = int(os.environ.get("DCB200_K1_STAGE", "0"))
 
 
 # Small host-built index tables (tile boundaries) uploaded once per distinct content and kept on the device: batches of a
