@@ -40,7 +40,7 @@ constexpr int T2_EPI_ROW = 20;                                // staging row: 16
 constexpr int T2_EPI_WARP_FLOATS = 32 * T2_EPI_ROW;
 constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOATS * 4 + 256 + 1024;
 constexpr int T2_DRAIN_KB = 4;                                // chain length in k-blocks (16 main MMA steps), long contractions
-constexpr int T2_DRAIN_KB_SHORT = 1;                          // ... short contractions (kb_total <= T2_SHORT_KB)
+constexpr int T2_DRAIN_KB_SHORT = 4;                          // ... short contractions (kb_total <= T2_SHORT_KB); lab knob
 constexpr int T2_SHORT_KB = 16;                               // K <= 512
 constexpr int T2_MAX_KPARTS = 64;   // weight gradients: 256 x 256 outputs over 512k nodes need ~37 parts to fill 148 SMs
 
@@ -516,8 +516,9 @@ int make_map2(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t rows,
 
 // Chain length in k-blocks.  The tensor core rounds its fp32 accumulator towards zero on every MMA, a bias of ~0.5 ulp per
 // MMA on the main (hi x hi) chain: 32 MMAs per chain gave 0.8-1.0e-6 against fp64 (round 1), 16 give 4.6e-7, 4 give ~3e-7
-// (profiles/r02_gemm_drain_lab.txt).  Short contractions (K <= 512: the attention scores Q K^T and dP = dO Xr^T, whose
-// ABSOLUTE error the unscaled softmax and its backward amplify) drain every k-block; long ones every T2_DRAIN_KB.
+// (profiles/r02_gemm_drain_lab.txt).  A separate length for short contractions (K <= 512: the attention scores Q K^T and
+// dP = dO Xr^T, whose absolute error the unscaled softmax amplifies) was measured too: no gain, so both classes use 4
+// (DCB200_DRAIN_KB / DCB200_DRAIN_KB_SHORT remain as lab knobs).
 int t2_drain_kb(int64_t kb_total) {
   static int d_long = -1, d_short = -1;
   if (d_long < 0) {

