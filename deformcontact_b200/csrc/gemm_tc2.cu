@@ -42,6 +42,7 @@ constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOAT
 constexpr int T2_DRAIN_KB = 4;                                // chain length in k-blocks (16 main MMA steps), long contractions
 constexpr int T2_DRAIN_KB_SHORT = 4;                          // ... short contractions (kb_total <= T2_SHORT_KB); lab knob
 constexpr int T2_SHORT_KB = 16;                               // K <= 512
+constexpr int T2_PART_KB = 8;                                 // k parts are whole multiples of 8 k-blocks (independent of the chain length)
 constexpr int T2_MAX_KPARTS = 64;   // weight gradients: 256 x 256 outputs over 512k nodes need ~37 parts to fill 148 SMs
 
 // one problem of a batched launch (device table; the tensor maps are read by TMA straight from global memory)
@@ -72,7 +73,9 @@ struct T2Params {
   const float* bias;
   int relu, accumulate;
   float* partial;         // [k_parts, M, N] when k_parts > 1
-  int raw_hi;             // 1: the MMA reads the raw fp32 tile as the hi operand (the tensor core ignores the low 13 bits)
+  int raw_hi;             // 1: the MMA reads the raw fp32 tile as the hi operand (the tensor core ignores the low 13 bits); 0: masked copy
+  int lo_rn;              // 1: lo = x - hi is pre-biased by half a tf32 ulp, so the tensor core's truncation rounds it to nearest
+  float comp;             // per-MMA compensation of the accumulator's round-towards-zero bias (0 = off); see t2_numerics()
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -118,11 +121,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint32_t rn_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -332,6 +330,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   } else if (warp >= 8 && warp < 12) {
     // ------------------------------------------------------------------ split warps: X -> X_hi (in place), X_lo
     const int t = threadIdx.x - 256;
+    const uint32_t rb = p.lo_rn ? 0x1000u : 0u;
     int it = 0, pidx = 0;
     for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
       const T2Item item = t2_item(p, w, pidx);
@@ -347,20 +346,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           uint4* src = (i & 1) ? b : a;
           const int idx = t + (i >> 1) * 128;
           const uint4 v = src[idx];
-          // raw_hi: the MMA reads the raw fp32 tile as hi, i.e. hi = trunc_tf32(x) (the tensor core ignores the low 13 bits);
-          // else hi = RN_tf32(x) is written back over the tile: |lo| halves and the dropped lo*lo term loses its sign bias
-          const uint4 h = p.raw_hi ? make_uint4(v.x & 0xFFFFE000u, v.y & 0xFFFFE000u, v.z & 0xFFFFE000u, v.w & 0xFFFFE000u)
-                                   : make_uint4(rn_tf32(__uint_as_float(v.x)), rn_tf32(__uint_as_float(v.y)),
-                                                rn_tf32(__uint_as_float(v.z)), rn_tf32(__uint_as_float(v.w)));
-          // lo = RN_tf32(x - hi): the tensor core TRUNCATES a tf32 operand to its upper 19 bits, so an unrounded
-          // remainder would lose up to 2^-10 of itself, always towards zero — a systematic shrink of both cross terms
-          // (2 x 2^-22 relative on average, the larger part of the 0.8-1.2e-6 error measured in round 1).  Rounded to
-          // nearest here, the remainder's error is unbiased and the truncation finds only zeros to drop.
+          // Branch-free on purpose: this loop is the critical path of the kernel, fully unrolled so that all 16 shared-memory
+          // loads are in flight before the first use; an if / else around the arithmetic serialised them and cost 17 % of the
+          // kernel (A/B against the round-1 build on the same box, profiles/r02_gemm_ab.txt).
+          //   hi = trunc_tf32(x): the raw tile itself serves as hi (the tensor core ignores the low 13 bits of a tf32 operand);
+          //   lo = (x - hi) + rb on the bit pattern: rb = 0x1000 pre-biases the remainder by half a tf32 ulp, so that the same
+          //        truncation rounds lo to nearest (ties away) instead of towards zero: the cross terms lose their systematic
+          //        shrink for one integer add per element (a cvt.rna.tf32 here is quarter-rate and cost 17 % as well).
+          const uint4 h = make_uint4(v.x & 0xFFFFE000u, v.y & 0xFFFFE000u, v.z & 0xFFFFE000u, v.w & 0xFFFFE000u);
           uint4 l;
-          l.x = rn_tf32(__uint_as_float(v.x) - __uint_as_float(h.x));
-          l.y = rn_tf32(__uint_as_float(v.y) - __uint_as_float(h.y));
-          l.z = rn_tf32(__uint_as_float(v.z) - __uint_as_float(h.z));
-          l.w = rn_tf32(__uint_as_float(v.w) - __uint_as_float(h.w));
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) + rb;
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) + rb;
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) + rb;
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) + rb;
           if (!p.raw_hi) src[idx] = h;
           src[idx + LO] = l;
         }
@@ -387,6 +385,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         mbar_wait(tfull_bar(j), (chain >> 1) & 1);
         tc_fence_after();
         const uint32_t cbase = lane_addr + (uint32_t)(2 * T2_BN * j);
+        // the main chain just drained went through 4 MMAs per k-block, each rounding the accumulator towards zero
+        const float comp = 1.0f + p.comp * (float)(4 * (min(item.kb1, kc0 + p.drain_kb) - kc0));
         uint32_t r[32];
 #pragma unroll
         for (int part = 0; part < 4; ++part) {   // main columns 0-31, 32-63 of this warp's half, then the cross-term columns
@@ -396,8 +396,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             tc_fence_before();
             mbar_arrive(tempty_bar(j));   // the accumulator pair is free again as soon as it sits in registers
           }
+          if (part < 2) {   // main (hi x hi) columns: add the chain with its expected truncation loss given back
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[(part & 1) * 32 + i] += __uint_as_float(r[i]);
+            for (int i = 0; i < 32; ++i) acc[(part & 1) * 32 + i] = fmaf(__uint_as_float(r[i]), comp, acc[(part & 1) * 32 + i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[(part & 1) * 32 + i] += __uint_as_float(r[i]);
+          }
         }
       }
       // ---- write the 32 x 64 block of this warp, 16 columns at a time through a padded staging tile
@@ -530,11 +535,34 @@ int t2_drain_kb(int64_t kb_total) {
   return kb_total <= T2_SHORT_KB ? (d_short < d_long ? d_short : d_long) : d_long;
 }
 
+// Numerics of the split and of the TMEM accumulation (both measured in profiles/r02_gemm_numerics_lab.txt):
+//  * lo_rn: the tensor core truncates tf32 operands; pre-biasing the lo remainder by half a tf32 ulp turns that into
+//    round-to-nearest (the hi part is the raw tile itself and stays truncated).
+//  * comp: the tensor core rounds its fp32 accumulator TOWARDS ZERO on every MMA.  One such rounding loses u * ulp(acc) with
+//    u ~ U[0, 1): 0.5 * 2^-23 * E[1/mantissa] = 4.3e-8 of |acc| on average.  Over a chain of n MMAs whose partial sums grow
+//    from 0 to x (|acc_t| / |x| ~ t/n for sign-coherent products such as P Xr, ~ sqrt(t/n) for random signs) that is
+//    ~ 0.6 n * 4.3e-8 |x|, always towards zero: a BIAS, which is what sum-with-cancellation reductions downstream (bias
+//    gradients, softmax backward) amplify.  The epilogue gives that expectation back when it adds a drained chain:
+//    acc += x * (1 + comp * n), comp = 2.6e-8.  Deterministic; exact when no rounding happened it over-corrects by at most
+//    comp * n = 4e-7 relative (n = 16), the size of the error it removes on dense data.
+void t2_numerics(T2Params& p) {
+  static int lo_rn = -1;
+  static float comp = -1.f;
+  if (lo_rn < 0) {
+    const char* e = getenv("DCB200_T2_LO_RN");
+    lo_rn = e ? (e[0] == '1') : 1;
+    const char* c = getenv("DCB200_T2_COMP");
+    comp = c ? (float)atof(c) : 2.6e-8f;
+  }
+  p.lo_rn = lo_rn;
+  p.comp = comp;
+}
+
 int t2_k_parts(int64_t M, int64_t N, int64_t kb_total) {
   const int64_t mn = cdiv(M, T2_BM) * cdiv(N, T2_BN);
   if (mn >= sm_count()) return 1;
   int64_t parts = sm_count() / mn;                          // fill the machine once
-  const int64_t max_parts = kb_total / T2_DRAIN_KB;   // at least one full chain per part
+  const int64_t max_parts = kb_total / T2_PART_KB;    // at least 8 k-blocks per part
   if (parts > max_parts) parts = max_parts;
   if (parts > T2_MAX_KPARTS) parts = T2_MAX_KPARTS;
   return parts < 1 ? 1 : (int)parts;
@@ -587,7 +615,7 @@ int gemm_tc2(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t 
   p.m_tiles = (int)cdiv(M, T2_BM);
   p.n_chunks = (int)cdiv(N, T2_BN);
   p.k_parts = t2_k_parts(M, N, p.kb_total);
-  p.kb_per_part = (int)(cdiv(cdiv(p.kb_total, p.k_parts), T2_DRAIN_KB) * T2_DRAIN_KB);   // whole chains per part
+  p.kb_per_part = (int)(cdiv(cdiv(p.kb_total, p.k_parts), T2_PART_KB) * T2_PART_KB);   // whole chains per part
   p.k_parts = (int)cdiv(p.kb_total, p.kb_per_part);
   p.items = p.m_tiles * p.n_chunks * p.k_parts;
   p.drain_kb = t2_drain_kb(p.kb_total);
@@ -596,6 +624,7 @@ int gemm_tc2(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t 
   // upper 19 bits of a tf32 operand), 7-10 % faster without the extra shared-memory write
   p.raw_hi = 1;
   if (const char* e = getenv("DCB200_T2_RAWHI")) p.raw_hi = e[0] == '1';
+  t2_numerics(p);
   if (p.k_parts > 1) {
     const size_t need = align_up((size_t)p.k_parts * M * N * sizeof(float), 256) + 256;
     DC_REQUIRE(workspace && workspace_bytes >= need, DC_EWORKSPACE, "gemm_tc2: workspace %zu < %zu", workspace_bytes, need);
@@ -696,6 +725,7 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
   p.relu = relu; p.accumulate = accumulate;
   p.raw_hi = 1;
   if (const char* e = getenv("DCB200_T2_RAWHI")) p.raw_hi = e[0] == '1';
+  t2_numerics(p);
   static DeviceOnce attr_set;
   if (attr_set.first()) {
     DC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));

@@ -13,8 +13,9 @@ tables of K1 are device-cached (ops._device_table), the problem tables of ``dc_g
 buffers this object keeps alive, and the optimizer runs in its capturable form.  Replays are bit-identical to the eager
 step (tests/test_gpu_train_loop.py, tests/test_gpu_step.py).
 
-The NCCL all-reduce of the flat gradient buffer is captured into the same graph (NCCL supports stream capture); if that
-capture fails the step falls back to two graphs with the collective issued eagerly in between.
+Data parallel: by default the step is two graphs (forward + backward | Adam) around an eager NCCL all-reduce of the flat
+gradient buffer; ``DCB200_GRAPH_ALLREDUCE=1`` captures the collective into one graph with the rest (NCCL supports stream
+capture; falls back to the two-graph form if the capture fails).
 """
 import os
 
@@ -23,7 +24,9 @@ import torch
 from . import _abi, ops
 from .model import fused_losses
 
-GRAPH_ALL_REDUCE = os.environ.get("DCB200_GRAPH_ALLREDUCE", "1") != "0"
+# 1: capture the NCCL all-reduce into the step's graph; 0 (default): two graphs around an eager all-reduce — three host calls
+# per step instead of one (~20 us), and no dependence on NCCL's stream-capture support at a rank count that was not tested
+GRAPH_ALL_REDUCE = os.environ.get("DCB200_GRAPH_ALLREDUCE", "0") != "0"
 
 
 def _clone_batch(b):

@@ -34,7 +34,9 @@ for M, N, K, ta, tb, label in shapes:
     Ar = (A[:, rows].T if ta else A[rows]).double()
     ref = Ar @ (B.double().T if tb else B.double())
     err = ((out[rows].double() - ref).abs().max() / ref.abs().max()).item()
+    big = ref.abs() > 0.25 * ref.abs().max()      # signed relative error where |C| is large: < 0 = systematic shrink (RZ accumulate)
+    bias = (((out[rows].double() - ref) / ref)[big]).mean().item()
     fn32 = lambda: ops.gemm([(A, B)], M, N, trans_a=ta, trans_b=tb, out=out, precision=dc._abi.GEMM_FP32)
     ms32 = t(fn32, 2)
     err32 = ((out[rows].double() - ref).abs().max() / ref.abs().max()).item()
-    print(f"{label:10s} {M}x{N}x{K}: tc {ms:.3f} ms {2.0*M*N*K/ms/1e9:.1f} TF/s err {err:.2e} | fp32 simt {ms32:.3f} ms {2.0*M*N*K/ms32/1e9:.1f} TF/s err {err32:.2e}")
+    print(f"{label:10s} {M}x{N}x{K}: tc {ms:.3f} ms {2.0*M*N*K/ms/1e9:.1f} TF/s err {err:.2e} bias {bias:+.1e} | fp32 simt {ms32:.3f} ms {2.0*M*N*K/ms32/1e9:.1f} TF/s err {err32:.2e}")
