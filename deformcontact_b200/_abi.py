@@ -51,6 +51,7 @@ PROTOTYPES = {
     "dc_pack_edges": (_int, [_p, _p, _i64, _p, _p]),
     "dc_spmm_lean": (_int, [_p, _p, _p, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _int, _p, _int, _p, _i64, _i32, _p]),
     "dc_spmm_chain": (_int, [_p, _p, _p, C.POINTER(Hop), _i32, _i64, _i32, _int, _p, _i64, _i32, _p]),
+    "dc_spmm_stream": (_int, [_p, _p, C.POINTER(Hop), _i32, _i64, _i32, _p, _i64, _i32, _p]),
     "dc_spmm_stage_supported": (_int, [_i64, _i32]),
     "dc_spmm_stage": (_int, [_p, _p, _p, C.POINTER(Hop), _i32, _i64, _i32, _int, _p, _i64, _i32, _i64, _p]),
     "dc_blocks_workspace_bytes": (_sz, [_i64]),

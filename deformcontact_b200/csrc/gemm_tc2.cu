@@ -380,6 +380,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       float acc[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      if (item.E != nullptr) {
+        // the fused epilogue operand of this warp's 32 x 64 block (2 lines per row): pull it into L2 while the tile's MMAs run
+        const int prow = item.m0 + q * 32 + lane;
+        const int pcol = item.n0 + half * 64;
+        if (prow < item.M && pcol < item.N) {
+          const float* pe = item.E + (long long)prow * item.lde + pcol;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pe));
+          if (pcol + 32 < item.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe + 32));
+        }
+      }
       for (int kc0 = item.kb0; kc0 < item.kb1; kc0 += p.drain_kb, ++chain) {
         const int j = chain & 1;
         mbar_wait(tfull_bar(j), (chain >> 1) & 1);
@@ -413,6 +423,52 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const bool do_relu = !to_slab && p.relu;
       const float* bias = to_slab ? nullptr : p.bias;
       const int row0 = item.m0 + q * 32;
+      if (item.E != nullptr && vec_ok && !add_c && !do_relu && !bias && (item.N & 3) == 0 && (item.lde & 3) == 0 &&
+          (reinterpret_cast<uintptr_t>(item.E) & 15) == 0) {
+        // ---- fused softmax backward  dS = P o (dP - rowsum(dP o P))  (E = P, rowv = rowdot(dO, O)): the operand loads of a
+        // 16-column group are issued one group AHEAD of the stores.  Inside the store loop the compiler has to keep them in
+        // program order behind the stores (C may alias E), which serialised 16 DRAM round trips per tile and ran this product
+        // at 89 TFLOP/s against 196 for its plain siblings (profiles/r02_launches_train_c3.csv, launch 294).
+        const int c4 = (lane & 3) * 4;
+        const int rsub = lane >> 2;
+        const int colbase = item.n0 + half * 64 + c4;
+        const float* erow = item.E + (long long)(row0 + rsub) * item.lde + colbase;
+        float* orow = outp + (long long)(row0 + rsub) * ldo + colbase;
+        float4 xa[4], xb[4];
+        float dv[4];
+#pragma unroll
+        for (int it4 = 0; it4 < 4; ++it4) dv[it4] = (row0 + it4 * 8 + rsub < item.M) ? __ldg(item.rowv + row0 + it4 * 8 + rsub) : 0.f;
+        auto load_group = [&](float4 (&x)[4], int g) {
+#pragma unroll
+          for (int it4 = 0; it4 < 4; ++it4) {
+            x[it4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + it4 * 8 + rsub < item.M && colbase + g * 16 < item.N)
+              x[it4] = __ldcs(reinterpret_cast<const float4*>(erow + (long long)(it4 * 8) * item.lde + g * 16));
+          }
+        };
+        load_group(xa, 0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+          for (int jv = 0; jv < 16; jv += 4)
+            *reinterpret_cast<float4*>(stg + lane * T2_EPI_ROW + jv) = make_float4(acc[g * 16 + jv], acc[g * 16 + jv + 1], acc[g * 16 + jv + 2], acc[g * 16 + jv + 3]);
+          __syncwarp();
+          if (g + 1 < 4) { if (g & 1) load_group(xa, g + 1); else load_group(xb, g + 1); }
+#pragma unroll
+          for (int it4 = 0; it4 < 4; ++it4) {
+            const int rr = it4 * 8 + rsub;
+            if (row0 + rr < item.M && colbase + g * 16 < item.N) {
+              float4 v = *reinterpret_cast<const float4*>(stg + rr * T2_EPI_ROW + c4);
+              const float4 e = (g & 1) ? xb[it4] : xa[it4];
+              const float d = dv[it4];
+              v.x = e.x * (v.x - d); v.y = e.y * (v.y - d); v.z = e.z * (v.z - d); v.w = e.w * (v.w - d);
+              *reinterpret_cast<float4*>(orow + (long long)(it4 * 8) * ldo + g * 16) = v;
+            }
+          }
+          __syncwarp();
+        }
+        continue;
+      }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
 #pragma unroll

@@ -146,6 +146,8 @@ K1_CHAIN = int(os.environ.get("DCB200_K1_CHAIN", "2"))
 # Measured r02 (C5, F=256, 2000-node graphs): 0.519 ms per forward hop against 0.348 for the L1 chain (the load and gather phases
 # of the one resident CTA do not overlap, and a 227 KB carve-out leaves ~28 KB of L1 for the edge records) -> off by default.
 K1_STAGE = int(os.environ.get("DCB200_K1_STAGE", "0"))
+# K1 v11: hop chains as per-group edge streams with a rolling gather window (dc_spmm_stream; no self loops, F % 32 == 0).
+K1_STREAM = int(os.environ.get("DCB200_K1_STREAM", "0"))
 
 
 # Small host-built index tables (tile boundaries) uploaded once per distinct content and kept on the device: batches of a
@@ -568,6 +570,9 @@ def spmm_chain(rowptr, edges, self_w, hops, self_loop=False, tile_ptr=None, n_ti
     if max_tile_rows:
         _abi.call("dc_spmm_stage", _ptr(rowptr), _ptr(edges), _ptr(self_w), arr, len(hops), N, F, int(bool(self_loop)),
                   _ptr(tile_ptr), int(n_tiles), int(tile_nodes), int(max_tile_rows), _stream())
+    elif K1_STREAM and not self_loop and F % 32 == 0:
+        _abi.call("dc_spmm_stream", _ptr(rowptr), _ptr(edges), arr, len(hops), N, F, _ptr(tile_ptr), int(n_tiles), int(tile_nodes),
+                  _stream())
     else:
         _abi.call("dc_spmm_chain", _ptr(rowptr), _ptr(edges), _ptr(self_w), arr, len(hops), N, F, int(bool(self_loop)), _ptr(tile_ptr),
                   int(n_tiles), int(tile_nodes), _stream())

@@ -135,6 +135,14 @@ DC_API int dc_spmm_stage_supported(int64_t max_tile_rows, int32_t F);
 DC_API int dc_spmm_stage(const int32_t* rowptr, const void* edges, const float* self_w, const dc_hop_t* hops, int32_t num_hops,
                          int64_t num_nodes, int32_t F, int self_loop, const int32_t* tile_ptr, int64_t n_tiles,
                          int32_t tile_nodes, int64_t max_tile_rows, dc_stream_t stream);
+/* K1 v11 (stream hop chain): the contract of dc_spmm_chain without self loops (TAGConv: gcn_norm(add_self_loops=False)).
+ * An 8-lane group owns a contiguous, cost-balanced range of the tile's receivers, walks its edges as ONE stream of packed
+ * records (prefetched into a shared-memory ring by cp.async) and keeps a rolling window of 8 row gathers in flight across
+ * receiver boundaries.  Same rows, records, order and rounding as dc_spmm_lean / dc_spmm_chain: bit-identical.  REQUIRES
+ * closed tiles when num_hops > 1 (like dc_spmm_chain), F % 32 == 0 and packed records (dc_pack_edges).
+ * Replaces: the K consecutive MessagePassing.propagate calls of one PyG TAGConv forward / backward (models/model.py:71,77). */
+DC_API int dc_spmm_stream(const int32_t* rowptr, const void* edges, const dc_hop_t* hops, int32_t num_hops, int64_t num_nodes,
+                          int32_t F, const int32_t* tile_ptr, int64_t n_tiles, int32_t tile_nodes, dc_stream_t stream);
 /* K1 v6 ("lean"): the same tile x 128-byte-slice mapping driven by packed 8-byte edge records
  * {int32 neighbour, fp32 weight} in CSR order (dc_pack_edges; w == NULL -> weight 1): one uniform 64-bit
  * load per edge instead of index/weight loads + shuffles, 8 row gathers in flight per lane, no predicates on

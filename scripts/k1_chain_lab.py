@@ -66,12 +66,26 @@ ms = ev_time(lambda: fwd_chain(buf_c, True), a.reps)
 res["fwd_chain_staged_v10"] = {"ms": round(ms, 4), "ms_per_hop": round(ms / 3, 4), "frac": round(3 * hop_bytes / (ms * 1e-3) / 1e9 / peak, 3), "bit_equal": ok_staged}
 print("fwd_chain_staged_v10", json.dumps(res["fwd_chain_staged_v10"]), flush=True)
 del buf_c
-for name, fn in (("fwd_3_launches", lambda: fwd_sep(buf_a)), ("fwd_chain", lambda: fwd_chain(buf_b))):
+def with_stream(flag, fn):
+    def run():
+        ops.K1_STREAM = flag
+        fn()
+    return run
+buf_d = torch.zeros(N, 3 * F, device=dev)
+with_stream(1, lambda: fwd_chain(buf_d))()
+ok_stream = torch.equal(buf_a, buf_d)
+del buf_d
+ops.K1_STREAM = 0
+for name, fn in (("fwd_3_launches", lambda: fwd_sep(buf_a)), ("fwd_chain", with_stream(0, lambda: fwd_chain(buf_b))),
+                 ("fwd_chain_stream_v11", with_stream(1, lambda: fwd_chain(buf_b)))):
+    if name.endswith("v11"):
+        ok = ok_stream
     ms = ev_time(fn, a.reps)
     res[name] = {"ms": round(ms, 4), "ms_per_hop": round(ms / 3, 4), "frac": round(3 * hop_bytes / (ms * 1e-3) / 1e9 / peak, 3), "bit_equal": ok}
     print(name, json.dumps(res[name]), flush=True)
 for hops in (1, 2):
     v = views(buf_b)
+    ops.K1_STREAM = int(os.environ.get("LAB_SHORT_STREAM", "1"))
     fn = lambda: ops.spmm_chain(G.rowptr, G.edges, None, [(x, None, v[0]), (v[0], None, v[1])][:hops], tile_ptr=G.tile_ptr, n_tiles=G.n_tiles)
     ms = ev_time(fn, a.reps)
     res[f"fwd_chain_{hops}hop"] = {"ms": round(ms, 4), "ms_per_hop": round(ms / hops, 4), "frac": round(hops * hop_bytes / (ms * 1e-3) / 1e9 / peak, 3)}
@@ -95,7 +109,9 @@ def bwd_chain(staged=False):
                        max_tile_rows=G._max_tile if staged else 0)
     return d, run
 outs = {}
-for name, (d, run) in (("T_3_blocks", bwd_sep("blocks")), ("T_3_lean", bwd_sep("lean")), ("T_chain", bwd_chain()), ("T_chain_staged_v10", bwd_chain(True))):
+for name, (d, run) in (("T_3_blocks", bwd_sep("blocks")), ("T_3_lean", bwd_sep("lean")), ("T_chain", bwd_chain()), ("T_chain_staged_v10", bwd_chain(True)),
+                       ("T_chain_stream_v11", bwd_chain())):
+    ops.K1_STREAM = 1 if name.endswith("v11") else 0
     if not name.startswith("T_chain"):
         ops.K1_VARIANT = name.split("_")[-1]
     run(); torch.cuda.synchronize()
@@ -105,7 +121,9 @@ for name, (d, run) in (("T_3_blocks", bwd_sep("blocks")), ("T_3_lean", bwd_sep("
     print(name, json.dumps(res[name]), flush=True)
 ops.K1_VARIANT = "auto"
 eq = (all(torch.equal(p, q) for p, q in zip(outs["T_3_blocks"], outs["T_chain"])) and all(torch.equal(p, q) for p, q in zip(outs["T_3_lean"], outs["T_chain"]))
-      and all(torch.equal(p, q) for p, q in zip(outs["T_chain_staged_v10"], outs["T_chain"])))
+      and all(torch.equal(p, q) for p, q in zip(outs["T_chain_staged_v10"], outs["T_chain"]))
+      and all(torch.equal(p, q) for p, q in zip(outs["T_chain_stream_v11"], outs["T_chain"])))
+ops.K1_STREAM = 1
 res["T_bit_equal"] = eq
 print("T_bit_equal", eq)
 if a.out:

@@ -370,11 +370,14 @@ def test_gemm_tcgen05_weight_gradient(dc, K, M, N):
     assert_close(acc, (2 * ref).float(), what="tcgen05 dW gemm accumulate")
 
 
+@pytest.mark.parametrize("stream", [0, 1])
 @pytest.mark.parametrize("F", [32, 256])
-def test_hop_chain_bit_identical_to_single_hops(dc, F):
-    """K1 v9: the hops of a layer in one launch == one launch per hop == generic kernel, bit for bit (forward and
-    transposed with in-place addends), ragged block-diagonal batch with isolated nodes, deep rows and an empty graph."""
+def test_hop_chain_bit_identical_to_single_hops(dc, F, stream, monkeypatch):
+    """K1 v9 (L1 chain) and K1 v11 (dc_spmm_stream: per-group edge streams, rolling gather window): the hops of a layer in
+    one launch == one launch per hop == generic kernel, bit for bit (forward and transposed with in-place addends), ragged
+    block-diagonal batch with isolated nodes, deep rows and an empty graph."""
     from deformcontact_b200 import ops
+    monkeypatch.setattr(ops, "K1_STREAM", stream)
     sizes = [700, 0, 1, 1300, 64]
     ptr = [0]
     for s_ in sizes:
