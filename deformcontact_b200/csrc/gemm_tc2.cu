@@ -381,13 +381,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = 0.f;
       if (item.E != nullptr) {
-        // the fused epilogue operand of this warp's 32 x 64 block (2 lines per row): pull it into L2 while the tile's MMAs run
-        const int prow = item.m0 + q * 32 + lane;
-        const int pcol = item.n0 + half * 64;
-        if (prow < item.M && pcol < item.N) {
-          const float* pe = item.E + (long long)prow * item.lde + pcol;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(pe));
-          if (pcol + 32 < item.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe + 32));
+        // The fused epilogue operand of a 32 x 64 block (2-3 lines per row) is pulled into L2 ONE ITEM AHEAD: with the fused
+        // epilogue this warp is the bottleneck of the tile pipeline (the MMAs of its current item are long done when it gets
+        // here), so a prefetch for the current item would be issued just before its first use.
+        auto prefetch_block = [&](const T2Item& it2) {
+          const int prow = it2.m0 + q * 32 + lane;
+          const int pcol = it2.n0 + half * 64;
+          if (it2.E != nullptr && prow < it2.M && pcol < it2.N) {
+            const float* pe = it2.E + (long long)prow * it2.lde + pcol;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pe));
+            if (pcol + 32 < it2.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe + 32));
+            if (pcol + 63 < it2.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe + 63));
+          }
+        };
+        if (w == (int)blockIdx.x) prefetch_block(item);
+        if (w + (int)gridDim.x < p.items) {
+          int pidx2 = pidx;
+          prefetch_block(t2_item(p, w + gridDim.x, pidx2));
         }
       }
       for (int kc0 = item.kb0; kc0 < item.kb1; kc0 += p.drain_kb, ++chain) {

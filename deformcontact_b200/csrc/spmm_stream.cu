@@ -27,7 +27,7 @@ namespace {
 constexpr int SS_CHUNK = 8;                       // records per cp.async chunk = one per lane of the group
 constexpr int SS_SLOTS = 4;                       // ring depth in chunks: consuming c, gathering from c + 1, c + 2 / c + 3 in flight
 constexpr int SS_RING = SS_CHUNK * SS_SLOTS;      // 32 records
-constexpr int SS_RING_BYTES = SS_RING * 8 + 8;    // + 8: consecutive groups start 2 banks apart (conflict-free broadcasts)
+constexpr int SS_RING_BYTES = SS_RING * 8 + 16;   // + 16: consecutive groups start 4 banks apart (conflict-free 16-byte broadcasts)
 constexpr int SS_ROW_WEIGHT = 2;                  // balancing key: edges + 2 * rows (a receiver costs about two edges: store + addend)
 
 struct StreamHops {
@@ -37,7 +37,7 @@ struct StreamHops {
   unsigned ldin[DC_MAX_CHAIN], ldadd[DC_MAX_CHAIN], ldout[DC_MAX_CHAIN];
 };
 
-__device__ __forceinline__ float4 ss_ld4(const float* p) {   // coherent: rows written earlier in this launch are read back
+__device__ __forceinline__ float4 ss_ld4(const char* p) {   // coherent: rows written earlier in this launch are read back
   float4 v;
   asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
@@ -54,17 +54,30 @@ __device__ __forceinline__ void ss_cp8(uint32_t dst, const void* src) {
 __device__ __forceinline__ void ss_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void ss_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ int4 ss_lds_rec2(uint32_t a) {   // two consecutive records (16-byte aligned)
+  int4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+  return r;
+}
 __device__ __forceinline__ int2 ss_lds_rec(uint32_t a) {
   int2 r;
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
   return r;
 }
 
-template <int THREADS>
+// BATCH = gathers per wait point.  The hardware tracks outstanding loads with six counting scoreboards per warp: a wait
+// on one of them returns when EVERY load assigned to it has landed, so a window refilled one load at a time (first version of
+// this kernel: 0.66 ms per hop against 0.35 for v9) makes each use wait for the load issued just before it.  The window is
+// therefore two batches: batch A is consumed (one wait) and refilled while batch B is in flight, and vice versa.
+template <int THREADS, int BATCH>
 __global__ void __launch_bounds__(THREADS, 1)
 spmm_stream_kernel(const int32_t* __restrict__ rowptr, const int2* __restrict__ edges, const StreamHops hops, int num_hops, int N,
                    const int32_t* __restrict__ tile_ptr, int n_slices, int tile_nodes) {
   constexpr int GROUPS = THREADS / 8;
+  constexpr int WIN = 2 * BATCH;                 // gather window in edges
+  constexpr int AHEAD = WIN / SS_CHUNK;          // the records gathered from in round c belong to chunk c + AHEAD
+  static_assert(BATCH == 4 || BATCH == 8, "batch of 4 or 8 gathers");
+  static_assert(AHEAD + 3 <= SS_SLOTS + 1 && SS_RING % WIN == 0, "ring too small");
   __shared__ __align__(16) unsigned char ring_mem[GROUPS * SS_RING_BYTES];
   __shared__ int bounds[GROUPS + 1];
 
@@ -98,37 +111,45 @@ spmm_stream_kernel(const int32_t* __restrict__ rowptr, const int2* __restrict__ 
   const int2* __restrict__ recs = edges + S0;
 
   for (int hop = 0; hop < num_hops; ++hop) {
-    const float* hcol = hops.in[hop] + col;
-    const size_t ldh = (size_t)hops.ldin[hop];
-    const float* add = hops.add[hop];
-    const size_t ldadd = (size_t)hops.ldadd[hop], ldo = (size_t)hops.ldout[hop];
-    float* out = hops.out[hop] + col;
-    if (add) add += col;
+    // byte pointers and 32-bit byte pitches: a row address is ONE IMAD.WIDE.U32
+    const char* hcol = reinterpret_cast<const char*>(hops.in[hop] + col);
+    const unsigned ldh = hops.ldin[hop] * 4u;
+    const char* add = reinterpret_cast<const char*>(hops.add[hop]);
+    const unsigned ldadd = hops.ldadd[hop] * 4u, ldo = hops.ldout[hop] * 4u;
+    char* out = reinterpret_cast<char*>(hops.out[hop] + col);
+    if (add) add += col * 4;
 
-    // ---- records: chunks 0, 1, 2 on their way before anything else
+    // ---- records: chunks 0 .. AHEAD + 1 on their way before anything else
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < AHEAD + 2; ++c) {
       const int q = c * SS_CHUNK + gl;
       if (q < len) ss_cp8(rb + (uint32_t)((q & (SS_RING - 1)) * 8), recs + q);
       ss_commit();
     }
-    int r = r0;                                                        // current receiver
-    int rend = 0, rend1 = 0;                                           // end of the current / next receiver's edges, relative to S0
+    // Receiver state: RAW absolute row ends (no arithmetic on a freshly loaded row pointer: the value is first needed one
+    // receiver later, when it has long landed) and running pointers (one add per receiver instead of an index multiply).
+    int rows_left = r1 - r0;                                           // receivers not yet stored, the current one included
+    int rend = 0x7fffffff, rend1 = 0x7fffffff;                         // end of the current / next receiver's edges (CSR positions)
+    const int32_t* rp_next = rowptr + r0 + 2;                          // row end to load at the next receiver change
+    char* out_row = out + (size_t)(unsigned)r0 * ldo;
+    const char* add_row = add ? add + (size_t)(unsigned)r0 * ldadd : nullptr;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), addn = acc;
-    if (r0 < r1) {
-      rend = __ldg(rowptr + r0 + 1) - S0;
-      if (r0 + 1 < r1) rend1 = __ldg(rowptr + r0 + 2) - S0;
+    if (rows_left > 0) {
+      rend = __ldg(rowptr + r0 + 1);
+      if (rows_left > 1) rend1 = __ldg(rp_next);
+      ++rp_next;
       if (add) {
-        acc = ss_ld4(add + (size_t)(unsigned)r0 * ldadd);
-        if (r0 + 1 < r1) addn = ss_ld4(add + (size_t)(unsigned)(r0 + 1) * ldadd);
+        acc = ss_ld4(add_row);
+        if (rows_left > 1) addn = ss_ld4(add_row + ldadd);
+        add_row += 2 * (size_t)ldadd;
       }
     }
-    ss_wait<2>();        // chunk 0 has landed
+    ss_wait<2>();        // chunks 0 .. AHEAD - 1 have landed
     __syncwarp();
-    float4 v[8];
-    float w[8];
+    float4 v[WIN];
+    float w[WIN];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < WIN; ++j) {
       v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       w[j] = 0.f;
       if (j < len) {
@@ -138,44 +159,86 @@ spmm_stream_kernel(const int32_t* __restrict__ rowptr, const int2* __restrict__ 
       }
     }
 
-    for (int c = 0; c * SS_CHUNK < len_max; ++c) {
-      ss_wait<1>();      // chunk c + 1 has landed (only chunk c + 2 may still be in flight)
-      __syncwarp();      // ... for every lane of the group; and every lane is done reading chunk c - 1 (the slot refilled below)
-      {
-        const int q = (c + 3) * SS_CHUNK + gl;
-        if (q < len) ss_cp8(rb + (uint32_t)((q & (SS_RING - 1)) * 8), recs + q);
-        ss_commit();
+    // receiver r is complete when the stream position reaches its end (the loop also walks over receivers without edges)
+    auto next_receiver = [&](int qa) {   // qa: CSR position of the edge about to be accumulated
+      while (qa >= rend) {
+        *reinterpret_cast<float4*>(out_row) = acc;
+        out_row += ldo;
+        acc = addn;
+        rend = rend1;
+        --rows_left;
+        if (rows_left > 1) {
+          rend1 = __ldg(rp_next);
+          if (add) addn = ss_ld4(add_row);
+        }
+        ++rp_next;
+        add_row += ldadd;
       }
+    };
+    for (int base = 0; base < len_max; base += WIN) {
+      const uint32_t ring_next = rb + (uint32_t)(((base + WIN) & (SS_RING - 1)) * 8);   // record of edge base + WIN (WIN | SS_RING)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int q = c * SS_CHUNK + j;
-        if (q < len) {
-          while (q >= rend) {   // receiver r is complete (also walks over receivers without edges)
-            *reinterpret_cast<float4*>(out + (size_t)(unsigned)r * ldo) = acc;
-            ++r;
-            acc = addn;
-            rend = rend1;
-            if (r + 1 < r1) {
-              rend1 = __ldg(rowptr + r + 2) - S0;
-              if (add) addn = ss_ld4(add + (size_t)(unsigned)(r + 1) * ldadd);
+      for (int h = 0; h < 2; ++h) {
+        if ((h * BATCH) % SS_CHUNK == 0) {   // a new chunk of 8 edges starts here (compile-time condition)
+          const int cc = (base + h * BATCH) / SS_CHUNK;
+          ss_wait<1>();      // chunk cc + AHEAD has landed (only the chunk after it may still be in flight)
+          __syncwarp();      // ... for every lane of the group; and every lane is done reading the slot refilled below
+          const int q = (cc + AHEAD + 2) * SS_CHUNK + gl;
+          if (q < len) ss_cp8(rb + (uint32_t)((q & (SS_RING - 1)) * 8), recs + q);
+          ss_commit();
+        }
+        if (base + WIN + (h + 1) * BATCH <= len) {
+          // ---- steady state: every edge of this batch and of its refill exists -> no per-edge predicates.
+          // Consume batch h (ONE wait for its BATCH gathers, issued a batch ago) ...
+#pragma unroll
+          for (int jj = 0; jj < BATCH; ++jj) {
+            const int j = h * BATCH + jj;
+            if (S0 + base + j >= rend) next_receiver(S0 + base + j);
+            ss_mul_add(acc, w[j], v[j]);
+          }
+          // ... and refill it with the gathers of the edges WIN further down the stream (records: chunk cc + AHEAD, landed)
+          int4 rec[BATCH / 2];   // two records per 16-byte shared-memory load: fewer loads in flight, fewer scoreboards taken
+#pragma unroll
+          for (int jj = 0; jj < BATCH / 2; ++jj) rec[jj] = ss_lds_rec2(ring_next + (uint32_t)((h * BATCH + 2 * jj) * 8));
+#pragma unroll
+          for (int jj = 0; jj < BATCH / 2; ++jj) {
+            const int j = h * BATCH + 2 * jj;
+            w[j] = __int_as_float(rec[jj].y);
+            v[j] = ss_ld4(hcol + (size_t)(unsigned)rec[jj].x * ldh);
+            w[j + 1] = __int_as_float(rec[jj].w);
+            v[j + 1] = ss_ld4(hcol + (size_t)(unsigned)rec[jj].z * ldh);
+          }
+        } else {
+          // ---- head / tail of the stream: the same with every edge predicated
+#pragma unroll
+          for (int jj = 0; jj < BATCH; ++jj) {
+            const int j = h * BATCH + jj;
+            const int q = base + j;
+            if (q < len) {
+              next_receiver(S0 + q);
+              ss_mul_add(acc, w[j], v[j]);
             }
           }
-          ss_mul_add(acc, w[j], v[j]);
-          const int q2 = q + 8;
-          if (q2 < len) {   // refill slot j with the gather of edge q + 8 (its record: chunk c + 1, landed)
-            const int2 rec = ss_lds_rec(rb + (uint32_t)((q2 & (SS_RING - 1)) * 8));
-            w[j] = __int_as_float(rec.y);
-            v[j] = ss_ld4(hcol + (size_t)(unsigned)rec.x * ldh);
+#pragma unroll
+          for (int jj = 0; jj < BATCH; ++jj) {
+            const int j = h * BATCH + jj;
+            if (base + j + WIN < len) {
+              const int2 rec = ss_lds_rec(ring_next + (uint32_t)(j * 8));
+              w[j] = __int_as_float(rec.y);
+              v[j] = ss_ld4(hcol + (size_t)(unsigned)rec.x * ldh);
+            }
           }
         }
       }
     }
     // ---- the last receiver with edges, and any trailing receivers without
-    while (r < r1) {
-      *reinterpret_cast<float4*>(out + (size_t)(unsigned)r * ldo) = acc;
-      ++r;
+    while (rows_left > 0) {
+      *reinterpret_cast<float4*>(out_row) = acc;
+      out_row += ldo;
       acc = addn;
-      if (r + 1 < r1 && add) addn = ss_ld4(add + (size_t)(unsigned)(r + 1) * ldadd);
+      --rows_left;
+      if (rows_left > 1 && add) addn = ss_ld4(add_row);
+      add_row += ldadd;
     }
     ss_wait<0>();
     __syncthreads();   // every row slice of this hop is stored (and visible to the block) before the next hop gathers it
@@ -219,23 +282,30 @@ extern "C" int dc_spmm_stream(const int32_t* rowptr, const void* edges, const dc
   }
   DC_REQUIRE(n_tiles > 0, DC_EINVAL, "spmm_stream: no tiles");
   const int n_slices = F / 32;
-  // 768 threads (96 groups, 80 registers, 25 KB of rings -> the 32 KB carve-out) is the default; DCB200_K1_STREAM_THREADS=1024
-  // selects 128 groups at 64 registers (34 KB of rings -> the 64 KB carve-out) for A/B runs (scripts/k1_chain_lab.py)
-  static int threads = 0;
-  if (!threads) {
-    const char* e = getenv("DCB200_K1_STREAM_THREADS");
-    threads = (e && atoi(e) == 1024) ? 1024 : DC_STREAM_THREADS;
+  // Configurations (A/B by DCB200_K1_STREAM_CFG, scripts/k1_chain_lab.py): threads x gathers per batch (window = 2 batches)
+  //   0: 768 x 4 (96 groups, 80 registers)   1: 1024 x 4 (128 groups, 64 registers)   2: 512 x 8 (64 groups, 16 in the window)
+  //   3: 512 x 4 (128 registers: nothing spilled or rematerialised)   4: 640 x 4
+  static int cfg = -1;
+  if (cfg < 0) {
+    const char* e = getenv("DCB200_K1_STREAM_CFG");
+    cfg = e ? atoi(e) : 0;
+    if (cfg < 0 || cfg > 4) cfg = 0;
   }
   static DeviceOnce carve;
-  if (carve.first()) {
-    cudaFuncSetAttribute(spmm_stream_kernel<768>, cudaFuncAttributePreferredSharedMemoryCarveout, 14);
-    cudaFuncSetAttribute(spmm_stream_kernel<1024>, cudaFuncAttributePreferredSharedMemoryCarveout, 28);
+  if (carve.first()) {   // static shared memory = record rings (264 B per group): ask for the smallest carve-out that holds them
+    cudaFuncSetAttribute(spmm_stream_kernel<768, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 14);
+    cudaFuncSetAttribute(spmm_stream_kernel<1024, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 28);
+    cudaFuncSetAttribute(spmm_stream_kernel<512, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 14);
+    cudaFuncSetAttribute(spmm_stream_kernel<512, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 14);
+    cudaFuncSetAttribute(spmm_stream_kernel<640, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 14);
   }
   const unsigned grid = (unsigned)(n_tiles * n_slices);
-  if (threads == 1024)
-    spmm_stream_kernel<1024><<<grid, 1024, 0, st>>>(rowptr, static_cast<const int2*>(edges), a, num_hops, (int)N, tile_ptr, n_slices, tile_nodes);
-  else
-    spmm_stream_kernel<768><<<grid, 768, 0, st>>>(rowptr, static_cast<const int2*>(edges), a, num_hops, (int)N, tile_ptr, n_slices, tile_nodes);
+  const int2* e2 = static_cast<const int2*>(edges);
+  if (cfg == 1) spmm_stream_kernel<1024, 4><<<grid, 1024, 0, st>>>(rowptr, e2, a, num_hops, (int)N, tile_ptr, n_slices, tile_nodes);
+  else if (cfg == 2) spmm_stream_kernel<512, 8><<<grid, 512, 0, st>>>(rowptr, e2, a, num_hops, (int)N, tile_ptr, n_slices, tile_nodes);
+  else if (cfg == 3) spmm_stream_kernel<512, 4><<<grid, 512, 0, st>>>(rowptr, e2, a, num_hops, (int)N, tile_ptr, n_slices, tile_nodes);
+  else if (cfg == 4) spmm_stream_kernel<640, 4><<<grid, 640, 0, st>>>(rowptr, e2, a, num_hops, (int)N, tile_ptr, n_slices, tile_nodes);
+  else spmm_stream_kernel<768, 4><<<grid, 768, 0, st>>>(rowptr, e2, a, num_hops, (int)N, tile_ptr, n_slices, tile_nodes);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
