@@ -472,7 +472,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
               const float4 e = (g & 1) ? xb[it4] : xa[it4];
               const float d = dv[it4];
               v.x = e.x * (v.x - d); v.y = e.y * (v.y - d); v.z = e.z * (v.z - d); v.w = e.w * (v.w - d);
-              *reinterpret_cast<float4*>(orow + (long long)(it4 * 8) * ldo + g * 16) = v;
+              // streaming store: 2 x 12.5 GB of P / dS pass through L2 per train step next to operand tiles that every CTA re-reads
+              __stcs(reinterpret_cast<float4*>(orow + (long long)(it4 * 8) * ldo + g * 16), v);
             }
           }
           __syncwarp();

@@ -17,10 +17,6 @@
 
 #include "common.cuh"
 
-#ifndef DC_STREAM_THREADS
-#define DC_STREAM_THREADS 768
-#endif
-
 namespace dcb {
 namespace {
 
@@ -288,8 +284,8 @@ extern "C" int dc_spmm_stream(const int32_t* rowptr, const void* edges, const dc
   static int cfg = -1;
   if (cfg < 0) {
     const char* e = getenv("DCB200_K1_STREAM_CFG");
-    cfg = e ? atoi(e) : 0;
-    if (cfg < 0 || cfg > 4) cfg = 0;
+    cfg = e ? atoi(e) : 4;   // 640 x 4 measured best (profiles/r02_k1_experiments.txt)
+    if (cfg < 0 || cfg > 4) cfg = 4;
   }
   static DeviceOnce carve;
   if (carve.first()) {   // static shared memory = record rings (264 B per group): ask for the smallest carve-out that holds them

@@ -173,7 +173,7 @@ def _device_table(key, build, device):
     return t
 
 
-TILE_WHOLE_MAX = 3600     # largest graph kept as ONE tile: what dc_spmm_stage can hold in shared memory (4 float4 lanes)
+TILE_WHOLE_MAX = int(os.environ.get("DCB200_TILE_WHOLE_MAX", "3600"))     # largest graph kept as ONE tile (3600: what dc_spmm_stage can hold in shared memory, 4 float4 lanes)
 
 
 def make_tiles(ptr_host, num_nodes, target=TILE_NODES, whole_max=TILE_WHOLE_MAX):

@@ -585,3 +585,7 @@ def test_relu_bwd_colsum_equals_the_two_kernels(dc, M, N):
     assert torch.equal(dX, ref) and torch.equal(dX, dY * (Y > 0))
     assert torch.equal(cs, ops.colsum(ref))
     assert_close(cs, ref.double().sum(0).float(), what="colsum")
+    # the float4 kernels (N % 4 == 0, aligned rows) and the scalar ones (same data behind a row pitch of N + 1) agree bit for bit
+    pad = lambda t: torch.cat([t, torch.zeros(M, 1, device="cuda")], 1)[:, :N]
+    dX2, cs2 = ops.relu_bwd_colsum(pad(Y), pad(dY))
+    assert torch.equal(dX2, dX) and torch.equal(cs2, cs) and torch.equal(ops.colsum(pad(ref)), cs)
