@@ -73,6 +73,7 @@ struct T2Params {
   const float* bias;
   int relu, accumulate;
   float* partial;         // [k_parts, M, N] when k_parts > 1
+  int pair;               // 1: launched as clusters of two CTAs driving one cta_group::2 MMA (template PAIR)
   int raw_hi;             // 1: the MMA reads the raw fp32 tile as the hi operand (the tensor core ignores the low 13 bits); 0: masked copy
   int lo_rn;              // 1: lo = x - hi is pre-biased by half a tf32 ulp, so the tensor core's truncation rounds it to nearest
   float comp;             // per-MMA compensation of the accumulator's round-towards-zero bias (0 = off); see t2_numerics()
@@ -122,6 +123,36 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA pair (cta_group::2): one MMA spans two SMs; the peer's threads signal barriers that live in the leader's shared memory
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_rank(uint32_t bar, uint32_t rank) {   // arrive on the barrier at the same offset in CTA `rank`
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((unsigned short)3)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -169,7 +200,9 @@ struct T2Item {
   long long lde;
 };
 // work item w of this CTA's sequence (w increases monotonically, so the problem index only moves forward)
-__device__ __forceinline__ T2Item t2_item(const T2Params& p, int w, int& pidx) {
+__device__ __forceinline__ T2Item t2_item(const T2Params& p, int w, int& pidx, int rank = 0) {
+  // p.pair: w counts PAIRS of row tiles (tile 2 q + rank for CTA `rank` of the cluster); a missing odd tile lies beyond M and
+  // is all zeros for TMA and all skipped rows for the epilogue
   T2Item it;
   if (p.batch) {
     while (w >= p.item_off[pidx + 1]) ++pidx;
@@ -178,7 +211,7 @@ __device__ __forceinline__ T2Item t2_item(const T2Params& p, int w, int& pidx) {
     const int nch = q->n_chunks;
     it.part = 0;
     it.n0 = (local % nch) * T2_BN;
-    it.m0 = (local / nch) * T2_BM;
+    it.m0 = (p.pair ? (local / nch) * 2 + rank : (local / nch)) * T2_BM;
     it.kb0 = 0;
     it.kb1 = q->kb_total;
     it.M = q->M; it.N = q->N; it.C = q->C; it.ldc = q->ldc;
@@ -189,7 +222,7 @@ __device__ __forceinline__ T2Item t2_item(const T2Params& p, int w, int& pidx) {
   it.part = w % p.k_parts;
   const int mn = w / p.k_parts;
   it.n0 = (mn % p.n_chunks) * T2_BN;
-  it.m0 = (mn / p.n_chunks) * T2_BM;
+  it.m0 = (p.pair ? (mn / p.n_chunks) * 2 + rank : (mn / p.n_chunks)) * T2_BM;
   it.kb0 = it.part * p.kb_per_part;
   it.kb1 = min(p.kb_total, it.kb0 + p.kb_per_part);
   it.M = p.M; it.N = p.N; it.C = p.C; it.ldc = p.ldc;
@@ -198,6 +231,7 @@ __device__ __forceinline__ T2Item t2_item(const T2Params& p, int w, int& pidx) {
   return it;
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
@@ -209,35 +243,57 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   float* epi_stage = reinterpret_cast<float*>(base_ptr + T2_STAGES * T2_STAGE_BYTES);
   const uint32_t bar_base = base + T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOATS * 4;
   // barriers (8 B each): full[3], xform[3], empty[3], tfull[2], tempty[2]; then the TMEM pointer
+  // A CTA of a pair holds half a B tile: 48 KB per stage instead of 64, so the same 192 KB make FOUR stages — the hand-offs that
+  // cross the pair (split warps -> leader's MMA thread, MMA commit -> both producers) take a few hundred cycles longer
+  constexpr int NST = PAIR ? 4 : T2_STAGES;
+  constexpr int STB = PAIR ? 3 * T2_TILE_BYTES : T2_STAGE_BYTES;
+  constexpr int B_OFF = 2 * T2_TILE_BYTES;                              // B hi (raw) behind A hi (raw), A lo
+  constexpr int BLO_OFF = PAIR ? B_OFF + T2_TILE_BYTES / 2 : B_OFF + T2_TILE_BYTES;   // B lo right behind B hi
+  static_assert(NST * STB == T2_STAGES * T2_STAGE_BYTES, "stage ring size");
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto xform_bar = [&](int s) { return bar_base + 24u + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 48u + 8u * s; };
-  auto tfull_bar = [&](int j) { return bar_base + 72u + 8u * j; };
-  auto tempty_bar = [&](int j) { return bar_base + 88u + 8u * j; };
+  auto xform_bar = [&](int s) { return bar_base + 32u + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
+  auto tfull_bar = [&](int j) { return bar_base + 96u + 8u * j; };
+  auto tempty_bar = [&](int j) { return bar_base + 112u + 8u * j; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOATS * 4 + 144);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // PAIR: the two CTAs of a cluster own row tiles 2 q and 2 q + 1 and HALF of the B tile each (64 of its 128 rows); CTA 0 (the
+  // leader) issues every MMA with cta_group::2 — M = 256 across the two SMs, each tensor core reading its own A tile and both B
+  // halves — so a CTA reads 2 KB of B per MMA instead of 4 and loads / splits 8 KB of B per k-block instead of 16.  The barriers
+  // the MMA thread waits on (xform, tempty) live in the leader and count the threads of both CTAs; what the MMA completes
+  // (empty, tfull) is committed to both CTAs at once.
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int w0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int wstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < T2_STAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(xform_bar(s), 128);
+      mbar_init(xform_bar(s), PAIR ? 8 : 128);      // PAIR: one (remote) arrival per split warp of both CTAs
       mbar_init(empty_bar(s), 1);
     }
     for (int j = 0; j < 2; ++j) {
       mbar_init(tfull_bar(j), 1);
-      mbar_init(tempty_bar(j), 256);
+      mbar_init(tempty_bar(j), PAIR ? 16 : 256);   // PAIR: one arrival per epilogue warp of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
+                   "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
+                   "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -247,8 +303,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const CUtensorMap* mA[4] = {&mapA0, &mapA1, &mapA2, &mapA3};
       const CUtensorMap* mB[4] = {&mapB0, &mapB1, &mapB2, &mapB3};
       int it = 0, pidx = 0, fenced = -1;
-      for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
-        const T2Item item = t2_item(p, w, pidx);
+      for (int w = w0; w < p.items; w += wstep) {
+        const T2Item item = t2_item(p, w, pidx, rank);
         if (p.batch) {
           mA[0] = item.mapA; mB[0] = item.mapB;
           if (fenced != pidx) {
@@ -265,18 +321,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           if (!p.batch)
             while (kb >= seg_kb0 + p.kb_seg[seg]) { seg_kb0 += p.kb_seg[seg]; ++seg; }
           const int k0 = (kb - seg_kb0) * T2_BK;
-          const int st = it % T2_STAGES;
-          const uint32_t ph = (it / T2_STAGES) & 1;
+          const int st = it % NST;
+          const uint32_t ph = (it / NST) & 1;
           mbar_wait(empty_bar(st), ph ^ 1);
-          const uint32_t sbase = base + st * T2_STAGE_BYTES;
-          mbar_expect_tx(full_bar(st), 2 * T2_TILE_BYTES);
+          const uint32_t sbase = base + st * STB;
+          mbar_expect_tx(full_bar(st), PAIR ? T2_TILE_BYTES + T2_TILE_BYTES / 2 : 2 * T2_TILE_BYTES);
           if (p.a_mn) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) tma_load_2d(sbase + c * 4096, mA[seg], full_bar(st), item.m0 + c * 32, k0);
           } else {
             tma_load_2d(sbase, mA[seg], full_bar(st), k0, item.m0);
           }
-          if (p.b_mn) {
+          if (PAIR) {   // this CTA's half of the B tile: rows [64 rank, 64 rank + 64) of the chunk (box of 64 rows / two 32-wide boxes)
+            const int nb0 = item.n0 + rank * (T2_BN / 2);
+            if (p.b_mn) {
+#pragma unroll
+              for (int c = 0; c < 2; ++c) tma_load_2d(sbase + 2 * T2_TILE_BYTES + c * 4096, mB[seg], full_bar(st), nb0 + c * 32, k0);
+            } else {
+              tma_load_2d(sbase + 2 * T2_TILE_BYTES, mB[seg], full_bar(st), k0, nb0);
+            }
+          } else if (p.b_mn) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) tma_load_2d(sbase + 2 * T2_TILE_BYTES + c * 4096, mB[seg], full_bar(st), item.n0 + c * 32, k0);
           } else {
@@ -286,8 +350,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (PAIR: the leader CTA only)
+    if (lane == 0 && rank == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                              ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
       const uint32_t a_adv = p.a_mn ? (1024u >> 4) : (32u >> 4), b_adv = p.b_mn ? (1024u >> 4) : (32u >> 4);
@@ -295,9 +359,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       // ONE MMA gives [ A_hi B_hi | A_hi B_lo ] in 256 adjacent TMEM columns; a second N = 128 MMA adds A_lo B_hi onto the
       // cross half.  2 MMAs and 20 KB of operand reads per K = 8 step instead of 3 and 24 KB.
       const uint32_t idesc256 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(2 * T2_BN >> 3) << 17);
+      // PAIR: M = 256 over the two CTAs, N = 128; three N = 128 MMAs per K = 8 step (the stacked [B_hi ; B_lo] form would interleave
+      // main and cross columns per CTA half, which a single N = 128 cross-term MMA cannot follow)
+      const uint32_t idesc_pair = (idesc & ~(0x1Fu << 24)) | ((uint32_t)(2 * T2_BM >> 4) << 24);
       int it = 0, chain = 0, pidx = 0;
-      for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
-        const T2Item item = t2_item(p, w, pidx);
+      for (int w = w0; w < p.items; w += wstep) {
+        const T2Item item = t2_item(p, w, pidx, rank);
         for (int kc0 = item.kb0; kc0 < item.kb1; kc0 += p.drain_kb, ++chain) {
           const int kc1 = min(item.kb1, kc0 + p.drain_kb);
           const int j = chain & 1;   // TMEM columns [256 j, 256 j + 128) main, [256 j + 128, 256 j + 256) cross terms
@@ -305,15 +372,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           mbar_wait(tempty_bar(j), ((chain >> 1) & 1) ^ 1);
           tc_fence_after();
           for (int kb = kc0; kb < kc1; ++kb, ++it) {
-            const int st = it % T2_STAGES;
-            const uint32_t ph = (it / T2_STAGES) & 1;
+            const int st = it % NST;
+            const uint32_t ph = (it / NST) & 1;
             mbar_wait(full_bar(st), ph);
-            mbar_wait(xform_bar(st), ph);
+            mbar_wait(xform_bar(st), ph);   // PAIR: both CTAs' tiles have landed and are split
             tc_fence_after();
-            const uint32_t sbase = base + st * T2_STAGE_BYTES;
+            const uint32_t sbase = base + st * STB;
             const uint64_t a_hi = p.a_mn ? desc_mnmajor(sbase) : desc_kmajor(sbase);
             const uint64_t a_lo = p.a_mn ? desc_mnmajor(sbase + T2_TILE_BYTES) : desc_kmajor(sbase + T2_TILE_BYTES);
             const uint64_t b_hi = p.b_mn ? desc_mnmajor(sbase + 2 * T2_TILE_BYTES) : desc_kmajor(sbase + 2 * T2_TILE_BYTES);
+            if (PAIR) {
+              const uint64_t b_lo = p.b_mn ? desc_mnmajor(sbase + BLO_OFF) : desc_kmajor(sbase + BLO_OFF);
+#pragma unroll
+              for (int kk = 0; kk < T2_BK / 8; ++kk) {
+                const uint64_t aa = (uint64_t)(kk * a_adv), bb = (uint64_t)(kk * b_adv);
+                const uint32_t acc = (kb > kc0 || kk > 0) ? 1u : 0u;
+                umma2_tf32(d_main, a_hi + aa, b_hi + bb, idesc_pair, acc);    // main  = A_hi B_hi
+                umma2_tf32(d_cross, a_hi + aa, b_lo + bb, idesc_pair, acc);   // cross = A_hi B_lo
+                umma2_tf32(d_cross, a_lo + aa, b_hi + bb, idesc_pair, 1u);    //       + A_lo B_hi
+              }
+              umma_commit2(empty_bar(st));
+            } else {
 #pragma unroll
             for (int kk = 0; kk < T2_BK / 8; ++kk) {
               const uint64_t aa = (uint64_t)(kk * a_adv), bb = (uint64_t)(kk * b_adv);
@@ -322,8 +401,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
               umma_tf32(d_cross, a_lo + aa, b_hi + bb, idesc, 1u);      // cross += A_lo B_hi
             }
             umma_commit(empty_bar(st));
+            }
           }
-          umma_commit(tfull_bar(j));
+          if (PAIR) umma_commit2(tfull_bar(j)); else umma_commit(tfull_bar(j));
         }
       }
     }
@@ -332,17 +412,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const int t = threadIdx.x - 256;
     const uint32_t rb = p.lo_rn ? 0x1000u : 0u;
     int it = 0, pidx = 0;
-    for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
-      const T2Item item = t2_item(p, w, pidx);
+    for (int w = w0; w < p.items; w += wstep) {
+      const T2Item item = t2_item(p, w, pidx, rank);
       for (int kb = item.kb0; kb < item.kb1; ++kb, ++it) {
-        const int st = it % T2_STAGES;
-        const uint32_t ph = (it / T2_STAGES) & 1;
+        const int st = it % NST;
+        const uint32_t ph = (it / NST) & 1;
         mbar_wait(full_bar(st), ph);
-        uint4* a = reinterpret_cast<uint4*>(base_ptr + st * T2_STAGE_BYTES);
-        uint4* b = reinterpret_cast<uint4*>(base_ptr + st * T2_STAGE_BYTES + 2 * T2_TILE_BYTES);
-        constexpr int LO = T2_TILE_BYTES / 16;   // the lo tile follows its hi tile
+        uint4* a = reinterpret_cast<uint4*>(base_ptr + st * STB);
+        uint4* b = reinterpret_cast<uint4*>(base_ptr + st * STB + B_OFF);
+        constexpr int LO = T2_TILE_BYTES / 16;   // the lo tile follows its hi tile (PAIR: half a B tile -> half the distance)
+        constexpr int LO_B = (BLO_OFF - B_OFF) / 16;
 #pragma unroll
         for (int i = 0; i < 2 * T2_TILE_BYTES / 16 / 128; ++i) {
+          if (PAIR && (i & 1) && (i >> 1) >= T2_TILE_BYTES / 32 / 128) continue;   // PAIR: half a B tile (8 KB)
           uint4* src = (i & 1) ? b : a;
           const int idx = t + (i >> 1) * 128;
           const uint4 v = src[idx];
@@ -360,10 +442,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) + rb;
           l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) + rb;
           if (!p.raw_hi) src[idx] = h;
-          src[idx + LO] = l;
+          src[idx + ((i & 1) ? LO_B : LO)] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(xform_bar(st));
+        if (PAIR) {
+          __syncwarp();   // every lane's tile writes (and its proxy fence) precede the one arrival of the warp
+          if (lane == 0) mbar_arrive_rank(xform_bar(st), 0);
+        } else {
+          mbar_arrive(xform_bar(st));
+        }
       }
     }
   } else if (warp >= 4) {
@@ -373,8 +460,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     float* stg = epi_stage + ((half * 4) + q) * T2_EPI_WARP_FLOATS;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
     int chain = 0, pidx = 0;
-    for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
-      const T2Item item = t2_item(p, w, pidx);
+    for (int w = w0; w < p.items; w += wstep) {
+      const T2Item item = t2_item(p, w, pidx, rank);
       const bool vec_ok = ((item.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(item.C) & 15) == 0) &&
                           (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) && ((item.N & 3) == 0 || p.k_parts == 1);
       float acc[64];
@@ -394,10 +481,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             if (pcol + 63 < it2.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe + 63));
           }
         };
-        if (w == (int)blockIdx.x) prefetch_block(item);
-        if (w + (int)gridDim.x < p.items) {
+        if (w == w0) prefetch_block(item);
+        if (w + wstep < p.items) {
           int pidx2 = pidx;
-          prefetch_block(t2_item(p, w + gridDim.x, pidx2));
+          prefetch_block(t2_item(p, w + wstep, pidx2, rank));
         }
       }
       for (int kc0 = item.kb0; kc0 < item.kb1; kc0 += p.drain_kb, ++chain) {
@@ -414,7 +501,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (part == 3) {
             tc_fence_before();
-            mbar_arrive(tempty_bar(j));   // the accumulator pair is free again as soon as it sits in registers
+            if (PAIR) {   // the accumulator pair is free again as soon as it sits in registers
+              __syncwarp();
+              if (lane == 0) mbar_arrive_rank(tempty_bar(j), 0);
+            } else {
+              mbar_arrive(tempty_bar(j));
+            }
           }
           if (part < 2) {   // main (hi x hi) columns: add the chain with its expected truncation loss given back
 #pragma unroll
@@ -533,10 +625,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: neither CTA may leave while the other can still signal its barriers
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -625,6 +718,44 @@ void t2_numerics(T2Params& p) {
   p.comp = comp;
 }
 
+// CTA pairs (cta_group::2) unless DCB200_T2_PAIR=0
+int t2_pair() {
+  static int pair = -1;
+  if (pair < 0) {
+    const char* e = getenv("DCB200_T2_PAIR");
+    pair = e ? (e[0] == '1') : 1;
+  }
+  return pair;
+}
+
+// one persistent CTA per SM; PAIR: clusters of two CTAs (an even grid)
+int t2_launch(const CUtensorMap* mA, const CUtensorMap* mB, const T2Params& p, cudaStream_t st) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
+    DC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    DC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+  }
+  if (!p.pair) {
+    const int grid = p.items < sm_count() ? p.items : sm_count();
+    gemm_tc2_kernel<false><<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(mA[0], mA[1], mA[2], mA[3], mB[0], mB[1], mB[2], mB[3], p);
+  } else {
+    const int pairs = p.items < sm_count() / 2 ? p.items : sm_count() / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(T2_THREADS);
+    cfg.dynamicSmemBytes = T2_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    DC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<true>, mA[0], mA[1], mA[2], mA[3], mB[0], mB[1], mB[2], mB[3], p));
+  }
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
 int t2_k_parts(int64_t M, int64_t N, int64_t kb_total) {
   const int64_t mn = cdiv(M, T2_BM) * cdiv(N, T2_BN);
   if (mn >= sm_count()) return 1;
@@ -659,6 +790,8 @@ int gemm_tc2(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t 
   p.nseg = nseg;
   p.a_mn = transA ? 1 : 0;
   p.b_mn = transB ? 0 : 1;
+  p.pair = t2_pair();
+  const uint32_t b_box_rows = p.pair ? T2_BN / 2 : T2_BN;   // a CTA of a pair loads half of the B tile
   CUtensorMap mA[4], mB[4];
   int64_t ktot = 0;
   for (int s = 0; s < 4; ++s) {
@@ -670,7 +803,7 @@ int gemm_tc2(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t 
       if (int rc = make_map2(&mA[s], segs[ss].A, K, (uint64_t)M, (uint64_t)segs[ss].lda, T2_BM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     }
     if (transB) {   // stored [N, K]: inner = K
-      if (int rc = make_map2(&mB[s], segs[ss].B, K, (uint64_t)N, (uint64_t)segs[ss].ldb, T2_BN, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+      if (int rc = make_map2(&mB[s], segs[ss].B, K, (uint64_t)N, (uint64_t)segs[ss].ldb, b_box_rows, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     } else {        // stored [K, N]: inner = N
       if (int rc = make_map2(&mB[s], segs[ss].B, (uint64_t)N, K, (uint64_t)segs[ss].ldb, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     }
@@ -684,7 +817,7 @@ int gemm_tc2(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t 
   p.k_parts = t2_k_parts(M, N, p.kb_total);
   p.kb_per_part = (int)(cdiv(cdiv(p.kb_total, p.k_parts), T2_PART_KB) * T2_PART_KB);   // whole chains per part
   p.k_parts = (int)cdiv(p.kb_total, p.kb_per_part);
-  p.items = p.m_tiles * p.n_chunks * p.k_parts;
+  p.items = (p.pair ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_chunks * p.k_parts;   // pair: items are pairs of row tiles
   p.drain_kb = t2_drain_kb(p.kb_total);
   p.C = C; p.ldc = ldc; p.bias = bias; p.relu = relu; p.accumulate = accumulate;
   // measured r01: identical error against fp64 with and without the masked copy (the tensor core reads only the
@@ -697,13 +830,7 @@ int gemm_tc2(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t 
     DC_REQUIRE(workspace && workspace_bytes >= need, DC_EWORKSPACE, "gemm_tc2: workspace %zu < %zu", workspace_bytes, need);
     p.partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   }
-  static DeviceOnce attr_set;
-  if (attr_set.first()) {
-    DC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
-  }
-  const int grid = p.items < sm_count() ? p.items : sm_count();
-  gemm_tc2_kernel<<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(mA[0], mA[1], mA[2], mA[3], mB[0], mB[1], mB[2], mB[3], p);
-  DC_LAUNCH_CHECK();
+  if (int rc = t2_launch(mA, mB, p, st)) return rc;
   if (p.k_parts > 1) {
     const long long MN = (long long)M * N;
     t2_reduce_kernel<<<(unsigned)cdiv(MN, 256), 256, 0, st>>>(p.partial, p.k_parts, MN, (int)N, C, ldc, bias, relu, accumulate);
@@ -742,6 +869,8 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
   unsigned char* hbase = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(hraw) + 63) & ~(uintptr_t)63);
   T2Problem* tab = reinterpret_cast<T2Problem*>(hbase);
   int* item_off = reinterpret_cast<int*>(hbase + tab_bytes);
+  const int pair = t2_pair();
+  const uint32_t b_box_rows = pair ? T2_BN / 2 : T2_BN;
   int64_t items = 0;
   int64_t max_kb = 0;
   for (int i = 0; i < count; ++i) {
@@ -761,7 +890,7 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
       if (int rc = make_map2(&t.mapA, q.A, (uint64_t)q.K, (uint64_t)q.M, (uint64_t)q.lda, T2_BM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     }
     if (transB) {
-      if (int rc = make_map2(&t.mapB, q.B, (uint64_t)q.K, (uint64_t)q.N, (uint64_t)q.ldb, T2_BN, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+      if (int rc = make_map2(&t.mapB, q.B, (uint64_t)q.K, (uint64_t)q.N, (uint64_t)q.ldb, b_box_rows, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     } else {
       if (int rc = make_map2(&t.mapB, q.B, (uint64_t)q.N, (uint64_t)q.K, (uint64_t)q.ldb, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     }
@@ -771,7 +900,7 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
     t.kb_total = (int)cdiv(q.K, T2_BK);
     if (t.kb_total > max_kb) max_kb = t.kb_total;
     t.n_chunks = (int)cdiv(q.N, T2_BN);
-    items += cdiv(q.M, T2_BM) * t.n_chunks;
+    items += (pair ? cdiv(cdiv(q.M, T2_BM), 2) : cdiv(q.M, T2_BM)) * t.n_chunks;
     DC_REQUIRE(items < (1ll << 30), DC_ENOSUP, "gemm_batched: too many work items");
   }
   item_off[count] = (int)items;
@@ -787,21 +916,15 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
   p.a_mn = transA ? 1 : 0;
   p.b_mn = transB ? 0 : 1;
   p.k_parts = 1;
+  p.pair = pair;
   p.items = (int)items;
   p.drain_kb = t2_drain_kb(max_kb);
   p.relu = relu; p.accumulate = accumulate;
   p.raw_hi = 1;
   if (const char* e = getenv("DCB200_T2_RAWHI")) p.raw_hi = e[0] == '1';
   t2_numerics(p);
-  static DeviceOnce attr_set;
-  if (attr_set.first()) {
-    DC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
-  }
-  const int grid = p.items < sm_count() ? p.items : sm_count();
-  CUtensorMap dummy{};
-  gemm_tc2_kernel<<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(dummy, dummy, dummy, dummy, dummy, dummy, dummy, dummy, p);
-  DC_LAUNCH_CHECK();
-  return DC_OK;
+  CUtensorMap dummy[4]{};
+  return t2_launch(dummy, dummy, p, st);
 }
 
 }  // namespace dcb
