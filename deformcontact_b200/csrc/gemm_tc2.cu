@@ -132,6 +132,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  __syncthreads();   // redundant for the hardware; compute-sanitizer's racecheck does not take the cluster barrier as a CTA barrier
 }
 __device__ __forceinline__ void mbar_arrive_rank(uint32_t bar, uint32_t rank) {   // arrive on the barrier at the same offset in CTA `rank`
   uint32_t remote;
@@ -531,8 +532,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         // 16-column group are issued one group AHEAD of the stores.  Inside the store loop the compiler has to keep them in
         // program order behind the stores (C may alias E), which serialised 16 DRAM round trips per tile and ran this product
         // at 89 TFLOP/s against 196 for its plain siblings (profiles/r02_launches_train_c3.csv, launch 294).
-        const int c4 = (lane & 3) * 4;
-        const int rsub = lane >> 2;
+        // lane -> (row, 16-byte column chunk) of the staged 32 x 16 block: the 8 lanes of a quarter-warp read 8 DIFFERENT rows at the
+        // same chunk (row pitch 80 B = 5 chunks: 5 r mod 8 is a permutation -> conflict-free); 4 chunks x 8 rows per store instruction
+        const int c4 = (lane >> 3) * 4;
+        const int rsub = lane & 7;
         const int colbase = item.n0 + half * 64 + c4;
         const float* erow = item.E + (long long)(row0 + rsub) * item.lde + colbase;
         float* orow = outp + (long long)(row0 + rsub) * ldo + colbase;
@@ -578,13 +581,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         for (int jv = 0; jv < 16; jv += 4)
           *reinterpret_cast<float4*>(stg + lane * T2_EPI_ROW + jv) = make_float4(acc[g * 16 + jv], acc[g * 16 + jv + 1], acc[g * 16 + jv + 2], acc[g * 16 + jv + 3]);
         __syncwarp();
-        const int c4 = (lane & 3) * 4;
+        const int c4 = (lane >> 3) * 4;   // see the fused path: conflict-free reads of the staging tile
         const int col = item.n0 + half * 64 + g * 16 + c4;
         if (vec_ok && col + 3 < item.N) {
           const float4 bv = bias ? *reinterpret_cast<const float4*>(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int it4 = 0; it4 < 4; ++it4) {
-            const int rr = it4 * 8 + (lane >> 2);
+            const int rr = it4 * 8 + (lane & 7);
             const int row = row0 + rr;
             if (row < item.M) {
               float4 v = *reinterpret_cast<const float4*>(stg + rr * T2_EPI_ROW + c4);
@@ -605,7 +608,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           }
         } else {
           for (int it4 = 0; it4 < 4; ++it4) {
-            const int rr = it4 * 8 + (lane >> 2);
+            const int rr = it4 * 8 + (lane & 7);
             const int row = row0 + rr;
             for (int e = 0; e < 4; ++e) {
               if (row < item.M && col + e < item.N) {

@@ -44,6 +44,16 @@ for Fs in (64, 24):
                    n_tiles=gc.n_tiles, max_tile_rows=gc._max_tile)
     ops.spmm_chain(gc.t[0], gc._edges_t, None, [(hx, hb[:, :Fs], hb[:, :Fs])], tile_ptr=gc.tile_ptr, n_tiles=gc.n_tiles,
                    max_tile_rows=gc._max_tile)
+# K1 v11 stream chain (cp.async record ring, two-batch gather window): forward and transposed in place, ragged tiles
+ops.K1_STREAM = 1
+hx = torch.randn(rest.x.shape[0], 64, device="cuda"); hb = torch.zeros(rest.x.shape[0], 192, device="cuda")
+ops.spmm_chain(gc.rowptr, gc.edges, None, [(hx, None, hb[:, :64]), (hb[:, :64], None, hb[:, 64:128]), (hb[:, 64:128], None, hb[:, 128:])],
+               tile_ptr=gc.tile_ptr, n_tiles=gc.n_tiles)
+ops.spmm_chain(gc.t[0], gc._edges_t, None, [(hx, hb[:, :64], hb[:, :64]), (hb[:, :64], hb[:, 64:128], hb[:, 64:128])], tile_ptr=gc.tile_ptr,
+               n_tiles=gc.n_tiles)
+ops.K1_STREAM = 0
+# float4 column sums
+ops.colsum(torch.randn(3000, 256, device="cuda")); ops.relu_bwd_colsum(torch.randn(3000, 256, device="cuda").relu(), torch.randn(3000, 256, device="cuda"))
 # fused ReLU backward + column sums; the captured train step (graph replay)
 ops.relu_bwd_colsum(torch.randn(3000, 100, device="cuda").relu(), torch.randn(3000, 100, device="cuda"))
 mg = dc.load_model(hidden_dim=64, attn_group=2).cuda()
