@@ -59,12 +59,15 @@ relu_bwd_colsum_stage1(const float* __restrict__ Y, int64_t ldy, const float* __
 }
 // float4 forms of the two stage-1 kernels (N % 4 == 0, 16-byte aligned rows): a thread owns 4 adjacent columns, so every global
 // access is 16 bytes per lane (512 contiguous bytes per warp and row) instead of 4.  Per column the rows are still summed by the
-// same 8 interleaved row lanes and the same tree: bit-identical to the scalar kernels.
-__global__ void __launch_bounds__(256)
+// same 8 interleaved row lanes and the same tree: bit-identical to the scalar kernels.  TXL = column lanes per block (32: 128 columns
+// per block; 8: 32 columns per block, four times the blocks — for short matrices, where 128-column blocks leave most SMs idle:
+// 64 blocks for the 64000 x 256 gradients of a 32-graph shard).
+template <int TXL>
+__global__ void __launch_bounds__(TXL * 8)
 colsum_stage1_v4(const float* __restrict__ X, int64_t ldx, int64_t M, int64_t N, float* __restrict__ partial) {
-  __shared__ float4 sm[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int64_t n = ((int64_t)blockIdx.x * 32 + tx) * 4;
+  __shared__ float4 sm[8][TXL + 1];
+  const int tx = threadIdx.x % TXL, ty = threadIdx.x / TXL;
+  const int64_t n = ((int64_t)blockIdx.x * TXL + tx) * 4;
   const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS;
   const int64_t r1 = min(M, r0 + CS_ROWS);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -84,12 +87,13 @@ colsum_stage1_v4(const float* __restrict__ X, int64_t ldx, int64_t M, int64_t N,
     *reinterpret_cast<float4*>(partial + (int64_t)blockIdx.y * N + n) = t;
   }
 }
-__global__ void __launch_bounds__(256)
+template <int TXL>
+__global__ void __launch_bounds__(TXL * 8)
 relu_bwd_colsum_stage1_v4(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ dY, int64_t lddy, float* __restrict__ dX,
                           int64_t lddx, int64_t M, int64_t N, float* __restrict__ partial) {
-  __shared__ float4 sm[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int64_t n = ((int64_t)blockIdx.x * 32 + tx) * 4;
+  __shared__ float4 sm[8][TXL + 1];
+  const int tx = threadIdx.x % TXL, ty = threadIdx.x / TXL;
+  const int64_t n = ((int64_t)blockIdx.x * TXL + tx) * 4;
   const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS;
   const int64_t r1 = min(M, r0 + CS_ROWS);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -280,8 +284,13 @@ extern "C" int dc_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, floa
   int64_t chunks = cdiv(M, CS_ROWS);
   DC_REQUIRE(chunks <= 65535, DC_ENOSUP, "colsum: M too large");
   if (N % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
-    dim3 grid4((unsigned)cdiv(N, 128), (unsigned)chunks);
-    colsum_stage1_v4<<<grid4, 256, 0, st>>>(X, ldx, M, N, static_cast<float*>(workspace));
+    if (cdiv(N, 128) * chunks >= 2 * sm_count()) {
+      dim3 grid4((unsigned)cdiv(N, 128), (unsigned)chunks);
+      colsum_stage1_v4<32><<<grid4, 256, 0, st>>>(X, ldx, M, N, static_cast<float*>(workspace));
+    } else {
+      dim3 grid4((unsigned)cdiv(N, 32), (unsigned)chunks);
+      colsum_stage1_v4<8><<<grid4, 64, 0, st>>>(X, ldx, M, N, static_cast<float*>(workspace));
+    }
   } else {
     dim3 grid((unsigned)cdiv(N, 32), (unsigned)chunks);
     colsum_stage1<<<grid, 256, 0, st>>>(X, ldx, M, N, static_cast<float*>(workspace));
@@ -304,8 +313,13 @@ extern "C" int dc_relu_bwd_colsum(const float* Y, int64_t ldy, const float* dY, 
   DC_REQUIRE(chunks <= 65535, DC_ENOSUP, "relu_bwd_colsum: M too large");
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (N % 4 == 0 && ldy % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && al16(Y) && al16(dY) && al16(dX) && al16(workspace)) {
-    dim3 grid4((unsigned)cdiv(N, 128), (unsigned)chunks);
-    relu_bwd_colsum_stage1_v4<<<grid4, 256, 0, st>>>(Y, ldy, dY, lddy, dX, lddx, M, N, static_cast<float*>(workspace));
+    if (cdiv(N, 128) * chunks >= 2 * sm_count()) {
+      dim3 grid4((unsigned)cdiv(N, 128), (unsigned)chunks);
+      relu_bwd_colsum_stage1_v4<32><<<grid4, 256, 0, st>>>(Y, ldy, dY, lddy, dX, lddx, M, N, static_cast<float*>(workspace));
+    } else {
+      dim3 grid4((unsigned)cdiv(N, 32), (unsigned)chunks);
+      relu_bwd_colsum_stage1_v4<8><<<grid4, 64, 0, st>>>(Y, ldy, dY, lddy, dX, lddx, M, N, static_cast<float*>(workspace));
+    }
   } else {
     dim3 grid((unsigned)cdiv(N, 32), (unsigned)chunks);
     relu_bwd_colsum_stage1<<<grid, 256, 0, st>>>(Y, ldy, dY, lddy, dX, lddx, M, N, static_cast<float*>(workspace));

@@ -573,7 +573,7 @@ def test_staged_hop_chain_unsupported_tile(dc):
     assert _abi.lib().dc_spmm_stage_supported(3500, 128)
 
 
-@pytest.mark.parametrize("M,N", [(1, 1), (5000, 256), (2049, 3), (777, 100)])
+@pytest.mark.parametrize("M,N", [(1, 1), (5000, 256), (2049, 3), (777, 100), (307300, 256)])   # last: the 128-column float4 blocks
 def test_relu_bwd_colsum_equals_the_two_kernels(dc, M, N):
     """dc_relu_bwd_colsum == dc_relu_bwd followed by dc_colsum, bit for bit (same summation order)."""
     from deformcontact_b200 import ops
