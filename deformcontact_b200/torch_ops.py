@@ -127,13 +127,20 @@ def tag_conv_backward(dout: Tensor, out: Tensor, x: Tensor, hops: Tensor, edge_i
         dws = dout.new_empty(0)
     db = db if need_db else dout.new_empty(0)
     if need_dx:
-        gk = ops.gemm([(dout, weights[K])], N, Fi, False, False, precision=precision)
         if ops.K1_CHAIN >= 2 and K > 0:
-            # all dH_k first, then the transposed hops as one chain, accumulating in place: dH_{k-1} += A_hat^T g_k
-            dhs = [ops.gemm([(dout, weights[k])], N, Fi, False, False, precision=precision) for k in range(K)] + [gk]
+            # all dH_k = dOut W_k first — ONE batched tensor-core launch over the K + 1 weights where the shapes allow it (same
+            # tiles and arithmetic as K + 1 dc_gemm calls, a quarter of the launches / pipeline ramps) — then the transposed hops as
+            # one chain, accumulating in place: dH_{k-1} += A_hat^T g_k
+            if (precision != ops.GEMM_FP32 and ops.FORCE_GEMM_PRECISION != ops.GEMM_FP32 and Fi % 4 == 0 and Fo % 4 == 0
+                    and float(N) * Fo * Fi >= 1.0e8 and all(w.stride(0) % 4 == 0 and w.data_ptr() % 16 == 0 for w in weights)):
+                dhs = [torch.empty((N, Fi), dtype=dout.dtype, device=dout.device) for _ in range(K + 1)]
+                ops.gemm_batched([(dout, weights[k], dhs[k]) for k in range(K + 1)], trans_a=False, trans_b=False)
+            else:
+                dhs = [ops.gemm([(dout, weights[k])], N, Fi, False, False, precision=precision) for k in range(K + 1)]
             ops.propagate_chain(g, [(dhs[k + 1], dhs[k], dhs[k]) for k in range(K - 1, -1, -1)], transpose=True, internal=True)
             gk = dhs[0]
         else:
+            gk = ops.gemm([(dout, weights[K])], N, Fi, False, False, precision=precision)
             for k in range(K - 1, -1, -1):
                 dhk = ops.gemm([(dout, weights[k])], N, Fi, False, False, precision=precision)
                 gk = g.propagate(gk, transpose=True, add=dhk, internal=True)
