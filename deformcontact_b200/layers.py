@@ -13,6 +13,8 @@ and cached) or a prebuilt ``ops.GraphCSR`` (adopted into that cache under its ow
 """
 import math
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -49,17 +51,20 @@ def _edge_tensor(edge_index):
     return edge_index
 
 
-def _pad4(x, weights):
+def _pad4(x, weights, chain=False):
     """Zero-pad the feature axis of ``x`` and the input axis of ``weights`` to a multiple of 4 floats (16-byte rows) so the
     vector hop kernels and the tensor-core GEMM take layers whose input width is not one (21 / 25 in everyday.json).
     The padding columns are exact zeros end to end; ``F.pad`` keeps autograd (the gradients are sliced back)."""
     pad = (-x.shape[1]) % 4
+    if chain and x.shape[1] < 32 and PAD_CHAIN_WIDTH:
+        pad = 32 - x.shape[1]      # one 128-byte slice: the K hops of the layer run as ONE chain launch (needs F % 32 == 0)
     if pad == 0 or not PAD_INPUT_WIDTH:
         return x, weights
     return nn.functional.pad(x, (0, pad)), [nn.functional.pad(w, (0, pad)) for w in weights]
 
 
 PAD_INPUT_WIDTH = True
+PAD_CHAIN_WIDTH = os.environ.get("DCB200_PAD_CHAIN", "1") == "1"   # TAGConv inputs narrower than 32 (21 / 25): pad to 32 instead of 24 / 28
 
 
 # ------------------------------------------------------------------------------- TAGConv
@@ -77,7 +82,7 @@ class TAGConv(nn.Module):
         self.precision = precision
 
     def forward(self, x, edge_index, relu=False, ptr=None):
-        x, ws = _pad4(x, [l.weight for l in self.lins])
+        x, ws = _pad4(x, [l.weight for l in self.lins], chain=True)
         return torch.ops.dcb200.tag_conv(x, _edge_tensor(edge_index), ws, self.bias, relu, self.normalize, self.precision, ptr)[0]
 
 

@@ -1,7 +1,14 @@
+# driver-like final check: GPU tests, smoke(), default bench line, reference arm
 mkdir -p gpurun_out
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 90000 --csv --log-file gpurun_out/launches_b32.csv \
-    python bench.py --global-batch 32 --steps 1 --warmup 3 --step eager --no-cpu-baseline --no-e2e --no-all-configs > gpurun_out/bench_under_ncu_b32.log 2>&1
-wc -l gpurun_out/launches_b32.csv
-python bench.py --global-batch 32 --steps 30 --no-all-configs --no-cpu-baseline --no-e2e 2>/dev/null | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('graph replay, 32 graphs:', round(d['ms_per_step'],3), 'ms/step', d.get('gpu_launches_per_step'), 'eager', d.get('eager_step_ms'))"
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+timeout 600 python -c "import __graft_entry__ as g; g.build(); g.smoke()" 2>&1 | tail -2
+timeout 900 python bench.py 2>gpurun_out/bench_default.err | tail -1 > gpurun_out/bench_default.json
+timeout 300 python bench.py --impl reference --steps 10 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_reference.json
+python - <<'PY'
+import json
+for f in ('bench_default','bench_reference'):
+    d=json.load(open('gpurun_out/%s.json'%f)); print(f, d['metric'], round(d['value'],2), d.get('e2e') and round(d['e2e']['value'],1), d.get('roofline') and d['roofline'].get('frac') and round(d['roofline']['frac'],3), d.get('roofline_k1') and round(d['roofline_k1']['frac'],3), d.get('gpu_launches'), round(d['ms_per_step'],2), d.get('our_kernel_ms_per_step'), d['clocks'] if 'clocks' in d else '')
+    if 'roofline' in d: print('  traffic', d['roofline'].get('traffic'), d['roofline_k1'].get('traffic'))
+    for k in ('c2','c4','c5'):
+        if k in d: print('  ', k, round(d[k]['value'],2), round(d[k]['ms_per_step'],2))
+PY
