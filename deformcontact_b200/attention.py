@@ -87,9 +87,15 @@ class _AttnFn(torch.autograd.Function):
         Nr = xr.shape[0]
         dev = xs.device
         douts = [d.contiguous() for d in douts]
-        dq = [torch.zeros((Ns, F), dtype=_f32, device=dev) for _ in range(H)]
-        dk = [torch.zeros((Nr, F), dtype=_f32, device=dev) for _ in range(H)]
-        dxr_h = [torch.zeros((Nr, F), dtype=_f32, device=dev) for _ in range(H)]
+        # every row of dq / dk / dxr_h inside a live group is written by the batched products below; only rows of groups that were
+        # skipped in forward (no resting or no rigid nodes) need zeros — none in a regular batch, so no full-size fills
+        cov_s = sum(s1 - s0 for s0, s1, _, _ in live) == Ns
+        cov_r = sum(r1 - r0 for _, _, r0, r1 in live) == Nr
+        new_s = torch.empty if cov_s else torch.zeros
+        new_r = torch.empty if cov_r else torch.zeros
+        dq = [new_s((Ns, F), dtype=_f32, device=dev) for _ in range(H)]
+        dk = [new_r((Nr, F), dtype=_f32, device=dev) for _ in range(H)]
+        dxr_h = [new_r((Nr, F), dtype=_f32, device=dev) for _ in range(H)]
         dPs = [[torch.empty((P.shape[0], P.stride(0)), dtype=_f32, device=dev)[:, :P.shape[1]] for P in probs[h]] for h in range(H)]
         HG = [(h, i, g) for h in range(H) for i, g in enumerate(live)]
         # softmax backward dS = P o (dP - rowsum(dP o P)) fused into the epilogue of dP = dO Xr^T: the row sums equal
