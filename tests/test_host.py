@@ -269,3 +269,30 @@ def test_gemm_segment_chunks_cover_every_segment():
     for n in range(1, 12):
         groups = [list(range(n))[i:i + _abi.MAX_SEGS] for i in range(0, n, _abi.MAX_SEGS)]
         assert sum(groups, []) == list(range(n)) and all(1 <= len(g) <= _abi.MAX_SEGS for g in groups)
+
+
+def test_narrow_tagconv_inputs_are_padded_to_one_chain_slice():
+    """layers._pad4: widths that are not a multiple of 4 get zero columns up to the next multiple (16-byte rows); TAGConv inputs
+    narrower than 32 (21 / 25 in configs/everyday.json) go to exactly 32 so that the layer's hops qualify for the chain kernel
+    (F % 32 == 0).  The padding is exact zeros on both operands, so x W^T is unchanged."""
+    from deformcontact_b200 import layers
+    x = torch.randn(7, 21)
+    ws = [torch.randn(5, 21) for _ in range(4)]
+    xp, wp = layers._pad4(x, ws, chain=True)
+    assert xp.shape == (7, 32) and all(w.shape == (5, 32) for w in wp)
+    assert torch.equal(xp[:, :21], x) and not xp[:, 21:].any() and not wp[0][:, 21:].any()
+    assert torch.allclose(xp @ wp[0].t(), x @ ws[0].t(), rtol=0, atol=1e-6)
+    xp, wp = layers._pad4(x, ws)                       # the other layers: next multiple of 4
+    assert xp.shape == (7, 24) and wp[0].shape == (5, 24)
+    x64 = torch.randn(3, 64)
+    assert layers._pad4(x64, ws, chain=True)[0] is x64  # nothing to do at hidden widths
+
+
+def test_attention_groups_partition_the_batch():
+    """attention._groups: consecutive groups of `attn_group` graphs (the reference's mini-batches); None = one group."""
+    from deformcontact_b200 import attention
+    ptr_s, ptr_r = [0, 10, 25, 25, 40, 60], [0, 3, 6, 9, 12, 15]
+    g = attention._groups(ptr_s, ptr_r, 2)
+    assert g == [(0, 25, 0, 6), (25, 40, 6, 12), (40, 60, 12, 15)]
+    assert attention._groups(ptr_s, ptr_r, None) == [(0, 60, 0, 15)]
+    assert sum(s1 - s0 for s0, s1, _, _ in g) == ptr_s[-1] and sum(r1 - r0 for _, _, r0, r1 in g) == ptr_r[-1]
