@@ -63,6 +63,17 @@ def _host_ptr(graph):
     return p
 
 
+BRANCH_STREAMS = os.environ.get("DCB200_BRANCH_STREAMS", "1") == "1"   # collider encoder branch on a second CUDA stream (0: one stream)
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 class GraphNet(nn.Module):
     def __init__(self, input_dims, hidden_dim, output_dim, encoder_layers, decoder_layers, dropout_rate, knn_k,
                  backbone, use_mha, num_mha_heads, mode, attn_group=None):
@@ -93,19 +104,31 @@ class GraphNet(nn.Module):
 
     def encode(self, graph_resting, graph_rigid):
         """models/model.py:69-78: x = dropout(relu(conv(x, edge_index))) per layer, both branches."""
-        x_resting = graph_resting.x
         ptr_rest = _host_ptr(graph_resting) if getattr(graph_resting, "ptr", None) is not None else None
         ptr_rigid = _host_ptr(graph_rigid) if getattr(graph_rigid, "ptr", None) is not None else None
-        for conv in self.conv_layers_resting:
-            x_resting = conv(x_resting, graph_resting.edge_index, relu=True, ptr=ptr_rest)
-            if self.dropout_rate > 0:
-                x_resting = F.dropout(x_resting, p=self.dropout_rate, training=self.training)
-        x_rigid = graph_rigid.x
-        for conv in self.conv_layers_rigid:
-            x_rigid = conv(x_rigid, graph_rigid.edge_index, relu=True, ptr=ptr_rigid)
-            if self.dropout_rate > 0:
-                x_rigid = F.dropout(x_rigid, p=self.dropout_rate, training=self.training)
-        return x_resting, x_rigid
+
+        def branch(convs, graph, ptr):
+            x = graph.x
+            for conv in convs:
+                x = conv(x, graph.edge_index, relu=True, ptr=ptr)
+                if self.dropout_rate > 0:
+                    x = F.dropout(x, p=self.dropout_rate, training=self.training)
+            return x
+
+        if BRANCH_STREAMS and graph_rigid.x.is_cuda:
+            # The two encoder branches are independent until the attention.  The collider branch is small (762-node graphs): on
+            # a second stream its latency-bound kernels (1-3 waves of tiles at 32 graphs per GPU) run next to the resting branch
+            # instead of in front of it; autograd replays each branch's backward on the stream of its forward.
+            main = torch.cuda.current_stream()
+            side = _side_stream(graph_rigid.x.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                x_rigid = branch(self.conv_layers_rigid, graph_rigid, ptr_rigid)
+            x_resting = branch(self.conv_layers_resting, graph_resting, ptr_rest)
+            main.wait_stream(side)
+            x_rigid.record_stream(main)   # allocated under `side`, consumed by the attention on `main`
+            return x_resting, x_rigid
+        return branch(self.conv_layers_resting, graph_resting, ptr_rest), branch(self.conv_layers_rigid, graph_rigid, ptr_rigid)
 
     def attend(self, x_resting, x_rigid, graph_resting, graph_rigid):
         G = self.attn_group
