@@ -301,3 +301,29 @@ def test_large_single_graph_runs_in_cell_order_with_identical_results():
         assert_close(wa, wb, what="dW reordered vs not")
     assert_close(a["db"], b["db"], what="db reordered vs not")
     assert a["loss"] == b["loss"]
+
+
+def test_encoder_branch_streams_do_not_change_a_bit(dc, monkeypatch):
+    """model.BRANCH_STREAMS: the collider encoder branch on a second CUDA stream (forward, and through autograd's per-op streams
+    backward) gives the same loss, prediction and gradients as the single-stream step, bit for bit, over several steps."""
+    from deformcontact_b200 import model as M
+    rest, rigid, deformed = synthetic.make_batch(4, 300, 8)
+    cu = lambda b: dc.Batch.from_data_list([dc.Data(x=d.x, edge_index=d.edge_index, pos=d.pos) for d in [b[i] for i in range(4)]]).to("cuda")
+    R, G, D = cu(rest), cu(rigid), cu(deformed)
+    res = []
+    for flag in (False, True):
+        monkeypatch.setattr(M, "BRANCH_STREAMS", flag)
+        torch.manual_seed(0)
+        net = dc.load_model(attn_group=2).cuda()
+        outs = []
+        for _ in range(3):
+            dc.ops.clear_csr_cache()
+            net.zero_grad()
+            loss, _, _ = dc.train_step_loss(net, R, G, D)
+            loss.backward()
+            torch.cuda.synchronize()
+            outs.append([loss.detach().clone()] + [p.grad.clone() for p in net.parameters()])
+        res.append(outs)
+    for a, b in zip(res[0], res[1]):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
