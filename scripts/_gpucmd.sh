@@ -1,5 +1,4 @@
-echo "== tests with DCB200_BRANCH_STREAMS=1"
-DCB200_BRANCH_STREAMS=1 timeout 900 python -m pytest tests/test_gpu_step.py tests/test_gpu_train_loop.py tests/test_gpu_layers.py -q -x 2>&1 | tail -2
-for bs in 1 0 1 0; do for b in 32 256; do DCB200_BRANCH_STREAMS=$bs python bench.py --global-batch $b --steps 20 --no-all-configs --no-cpu-baseline --no-e2e 2>/dev/null | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('branch_streams=$bs graphs $b:', round(d['ms_per_step'],3), 'ms/step')"; done; done
+mkdir -p gpurun_out
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc2_kernel -s 170 -c 1 -f -o gpurun_out/prof_gemm_step \
+    python bench.py --steps 1 --warmup 3 --step eager --no-cpu-baseline --no-e2e --no-all-configs > gpurun_out/ncu_gemm.log 2>&1
+tail -2 gpurun_out/ncu_gemm.log
