@@ -501,7 +501,11 @@ def run_ours(args):
 
     if rank == 0:
         cfg = config_dict(args, world)
-        cfg.update({"global_batch": Btot, "step_execution": mode})
+        from deformcontact_b200 import model as _dcm
+        cfg.update({"global_batch": Btot, "step_execution": mode,
+                    "streams": "collider encoder branch on a second CUDA stream (fork / join)" if _dcm.BRANCH_STREAMS else "one stream",
+                    "gemm": "tcgen05 kind::tf32 3-term split, CTA pairs (cta_group::2)" if os.environ.get("DCB200_T2_PAIR", "1") == "1"
+                            else "tcgen05 kind::tf32 3-term split, one CTA per tile"})
         line = {"metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": cfg,
