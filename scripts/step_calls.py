@@ -4,7 +4,8 @@ import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import deformcontact_b200 as dc
-from deformcontact_b200 import ops, synthetic
+from deformcontact_b200 import ops, synthetic, model as dcm
+dcm.BRANCH_STREAMS = False   # one stream: every call is timed alone
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--graphs", type=int, default=256)
