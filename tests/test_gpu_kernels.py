@@ -589,3 +589,29 @@ def test_relu_bwd_colsum_equals_the_two_kernels(dc, M, N):
     pad = lambda t: torch.cat([t, torch.zeros(M, 1, device="cuda")], 1)[:, :N]
     dX2, cs2 = ops.relu_bwd_colsum(pad(Y), pad(dY))
     assert torch.equal(dX2, dX) and torch.equal(cs2, cs) and torch.equal(ops.colsum(pad(ref)), cs)
+
+
+def test_gemm_cta_pairs_on_ragged_shapes(dc):
+    """K2 as CTA pairs (cta_group::2): odd numbers of row tiles (the peer CTA's tile lies beyond M), N < 64 (the peer's half of the
+    B tile is empty), K not a multiple of 32, every operand layout, single / split-K / batched launches — against fp64."""
+    import random
+    from deformcontact_b200 import ops
+    rnd = random.Random(1)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for trial in range(10):
+        M = rnd.choice([1, 127, 129, 257, 300, 385, 1000])
+        N = rnd.choice([4, 24, 60, 68, 132, 260, 520])
+        K = rnd.choice([4, 28, 36, 100, 260, 4100, 20000])
+        for ta in (False, True):
+            for tb in (False, True):
+                Mp, Np, Kp = (M + 3) // 4 * 4, (N + 3) // 4 * 4, (K + 3) // 4 * 4
+                A = torch.randn((K, Mp) if ta else (M, Kp), generator=g, device="cuda")[:, :M if ta else K]
+                B = torch.randn((N, Kp) if tb else (K, Np), generator=g, device="cuda")[:, :K if tb else N]
+                ref = ((A.double().t() if ta else A.double()) @ (B.double().t() if tb else B.double())).float()
+                out = ops.gemm([(A, B)], M, N, ta, tb, precision=ops.GEMM_TF32X3)
+                assert_close(out, ref, what=f"gemm {M}x{N}x{K} ta={ta} tb={tb}")
+                if trial % 3 == 0:
+                    outs = [torch.empty(M, N, device="cuda") for _ in range(2)]
+                    ops.gemm_batched([(A, B, o) for o in outs], ta, tb)
+                    for o in outs:
+                        assert_close(o, ref, what=f"gemm_batched {M}x{N}x{K} ta={ta} tb={tb}")
