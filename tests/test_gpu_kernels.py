@@ -434,6 +434,24 @@ def test_hop_chain_rejects_bad_args(dc):
         ops.spmm_chain(g.rowptr, g.edges, None, [(x, None, x)], tile_ptr=g.tile_ptr, n_tiles=g.n_tiles)
 
 
+def test_stream_chain_rejects_bad_args(dc, monkeypatch):
+    """dc_spmm_stream keeps the contract of dc_spmm_chain: F % 32 == 0, in != out; and self loops (GCN) never reach it."""
+    from deformcontact_b200 import ops, _abi
+    monkeypatch.setattr(ops, "K1_STREAM", 1)
+    ei = torch.randint(0, 100, (2, 500)).cuda()
+    g = ops.GraphCSR(ei, 100, "tag", [0, 100])
+    x = torch.randn(100, 24).cuda()
+    with pytest.raises(_abi.DcError):
+        ops.spmm_chain(g.rowptr, g.edges, None, [(x, None, torch.empty_like(x))], tile_ptr=g.tile_ptr, n_tiles=g.n_tiles)
+    x = torch.randn(100, 32).cuda()
+    with pytest.raises(_abi.DcError):
+        ops.spmm_chain(g.rowptr, g.edges, None, [(x, None, x)], tile_ptr=g.tile_ptr, n_tiles=g.n_tiles)
+    gg = ops.GraphCSR(ei, 100, "gcn", [0, 100])     # self loops: falls through to the v9 kernel, same numbers as single hops
+    out = torch.empty_like(x)
+    ops.spmm_chain(gg.rowptr, gg.edges, gg.self_w, [(x, None, out)], self_loop=True, tile_ptr=gg.tile_ptr, n_tiles=gg.n_tiles)
+    assert torch.equal(out, gg.propagate(x))
+
+
 def _clouds():
     g = torch.Generator().manual_seed(77)
     uni = torch.rand(6000, 3, generator=g) - 0.5
