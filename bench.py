@@ -735,13 +735,20 @@ def run_mesh_c4(args, emit=True):
     radius_edges = dc.radius_graph(pos, radius).shape[1]
     x0 = dc.to_log_freq(pos)
 
-    def fwd():
+    def fwd_loop():    # the reference's literal loop (models/model.py:69-72): every layer permutes into and out of the cell order
         ops.clear_csr_cache()
         x = x0
         with torch.no_grad():
             for layer in layers:
                 x = layer(x, ei, relu=True)
         return x
+
+    def fwd():         # dc.layer_stack: the same layers, features kept in the structure's node order from layer to layer
+        ops.clear_csr_cache()
+        with torch.no_grad():
+            return dc.layer_stack(list(layers), x0, ei, relu=True)
+    assert torch.equal(fwd(), fwd_loop())
+    mp_loop_ms = _ev_time(fwd_loop, args.steps, max(args.warmup, 3))
     l0 = dc._abi.lib().dc_launch_count()
     mp_ms = _ev_time(fwd, args.steps, max(args.warmup, 3))
     launches = (dc._abi.lib().dc_launch_count() - l0) // (args.steps + max(args.warmup, 3))
@@ -757,7 +764,7 @@ def run_mesh_c4(args, emit=True):
                       "knn_algorithm": "uniform grid (K4g), bit-identical to the brute-force kernel; includes the edge_index compaction "
                                        "and its host read of E",
                       "knn_brute_force_ms": knn_brute_ms, "knn_brute_force_pair_distances_per_sec": N * N / (knn_brute_ms * 1e-3),
-                      "mp_15_layers_ms": mp_ms,
+                      "mp_15_layers_ms": mp_ms, "mp_15_layers_per_layer_loop_ms": mp_loop_ms,
                       "radius_build_ms": radius_ms, "radius": radius, "radius_edges": int(radius_edges),
 
                       "edge_traversals_per_sec": 3 * L * E / (mp_ms * 1e-3)})

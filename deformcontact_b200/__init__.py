@@ -9,7 +9,7 @@ _abi.lib()  # fail loudly at import if the native library is absent
 
 from . import ops  # noqa: E402
 from .data import Data, Batch, collate_fn  # noqa: E402,F401
-from .layers import TAGConv, GCNConv, GATConv, MPNNLayer  # noqa: E402,F401
+from .layers import TAGConv, GCNConv, GATConv, MPNNLayer, layer_stack  # noqa: E402,F401
 from .graph import mesh_to_graph, knn_graph, radius_graph, construct_graph, to_log_freq  # noqa: E402,F401
 from .assemble import (batch_from_data_list, mesh_batch, collider_batch, collider_batch_device, graph_batch,  # noqa: E402,F401
                        graph_batch_packed, Staging)

@@ -86,6 +86,25 @@ class TAGConv(nn.Module):
         return torch.ops.dcb200.tag_conv(x, _edge_tensor(edge_index), ws, self.bias, relu, self.normalize, self.precision, ptr)[0]
 
 
+def layer_stack(layers, x, edge_index, relu=True, ptr=None, between=None):
+    """``for conv in layers: x = act(conv(x, edge_index))`` (models/model.py:69-78) for TAGConv / GCNConv layers on ONE graph.
+    A relabelled large graph (one cloud of >= 32768 points from ``knn_graph`` / ``radius_graph``) is entered once and left
+    once: its features stay in the structure's node order from layer to layer (bit-identical to the plain loop, which
+    permutes in and out of every layer).  ``between``: optional callable applied after every layer (dropout)."""
+    mode = {"TAGConv": "tag", "GCNConv": "gcn"}.get(type(layers[0]).__name__) if len(layers) else None
+    same = mode is not None and all(type(l) is type(layers[0]) for l in layers)
+    if mode == "tag" and same and not all(getattr(l, "normalize", True) for l in layers):
+        same = False
+    g = None
+    if same and not isinstance(edge_index, ops.GraphCSR):
+        x, edge_index, g = ops.stack_enter(x, edge_index, mode, ptr)
+    for conv in layers:
+        x = conv(x, edge_index, relu=relu, ptr=ptr)
+        if between is not None:
+            x = between(x)
+    return ops.stack_exit(x, g)
+
+
 # ------------------------------------------------------------------------------- GCNConv
 class GCNConv(nn.Module):
     """PyG ``GCNConv(in, out)`` defaults; keys ``lin.weight``, ``bias``."""

@@ -107,13 +107,10 @@ class GraphNet(nn.Module):
         ptr_rest = _host_ptr(graph_resting) if getattr(graph_resting, "ptr", None) is not None else None
         ptr_rigid = _host_ptr(graph_rigid) if getattr(graph_rigid, "ptr", None) is not None else None
 
+        drop = (lambda t: F.dropout(t, p=self.dropout_rate, training=self.training)) if self.dropout_rate > 0 else None
+
         def branch(convs, graph, ptr):
-            x = graph.x
-            for conv in convs:
-                x = conv(x, graph.edge_index, relu=True, ptr=ptr)
-                if self.dropout_rate > 0:
-                    x = F.dropout(x, p=self.dropout_rate, training=self.training)
-            return x
+            return layer_stack(list(convs), graph.x, graph.edge_index, relu=True, ptr=ptr, between=drop)
 
         if BRANCH_STREAMS and graph_rigid.x.is_cuda:
             # The two encoder branches are independent until the attention.  The collider branch is small (762-node graphs): on

@@ -6,6 +6,7 @@ where a data-dependent output size must be read back: ``knn_graph`` / ``radius_g
 PyTorch is plumbing here: device memory and streams.  No eager fallback exists.
 """
 import collections
+import copy
 import ctypes as C
 import weakref
 
@@ -318,6 +319,21 @@ class GraphCSR:
         self.tiles_closed = tiles is not None and set(tiles) <= set(ptr_host)
         self._blocks = {}
         self._max_tile = max((b - a for a, b in zip(tiles[:-1], tiles[1:])), default=0) if tiles is not None else TILE_NODES
+        self._view = None
+
+    def internal_view(self):
+        """The same structure seen as a graph whose nodes ARE numbered in this structure's order (``order`` None).  A stack of
+        layers on one relabelled graph permutes its input once, runs every layer on the view and permutes the result back
+        once (``stack_enter`` / ``stack_exit``) instead of twice per layer."""
+        if self.order is None:
+            return self
+        if self._view is None:
+            v = copy.copy(self)
+            v.order, v.rank, v._view = None, None, None
+            v._src_edge_index = self.edge_index      # the relabelled edge list: the tensor the view is cached under
+            v._blocks = {}
+            self._view = v
+        return self._view
 
     def blocks(self, transpose=False, unit=4):
         """K1 v7/v8 edge blocks (sliced-ELL copy of the CSR) of the forward / transposed structure, built lazily."""
@@ -442,6 +458,35 @@ def adopt_csr(g):
 
 def clear_csr_cache():
     _CSR_CACHE.clear()
+
+
+class _PermuteRows(torch.autograd.Function):
+    """out[i] = x[perm[i]] with its exact adjoint (dx = dout[inverse]); both through dc_permute_rows."""
+
+    @staticmethod
+    def forward(ctx, x, perm, inverse):
+        ctx.inverse = inverse
+        return permute_rows(x.contiguous(), perm)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return permute_rows(dout.contiguous(), ctx.inverse), None, None
+
+
+def stack_enter(x, edge_index, mode="tag", ptr_host=None):
+    """Entry of a stack of layers that all run on ``edge_index`` (models/model.py:69-78).  For a relabelled large graph
+    (``GraphCSR.order``) returns the features in the structure's node order, the relabelled edge list (with the structure's
+    internal view adopted into the cache, so the layers neither rebuild nor permute) and the structure to leave through;
+    otherwise the arguments unchanged and None."""
+    g = edge_index if isinstance(edge_index, GraphCSR) else graph_csr(edge_index, x.shape[0], mode, ptr_host)
+    if g.order is None:
+        return x, edge_index, None
+    return _PermuteRows.apply(x, g.order, g.rank), adopt_csr(g.internal_view()), g
+
+
+def stack_exit(y, g):
+    """Back to the caller's node order (identity when ``stack_enter`` returned None)."""
+    return y if g is None else _PermuteRows.apply(y, g.rank, g.order)
 
 
 # ----------------------------------------------------------------------------- K1

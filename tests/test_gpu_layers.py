@@ -303,6 +303,47 @@ def test_large_single_graph_runs_in_cell_order_with_identical_results():
     assert a["loss"] == b["loss"]
 
 
+@pytest.mark.parametrize("kind", ["TAGConv", "GCNConv"])
+def test_layer_stack_keeps_the_cell_order_between_layers_bit_for_bit(kind):
+    """dc.layer_stack (models/model.py:69-78 on one relabelled large graph): features enter the structure's node order once and
+    leave it once.  Outputs and input gradients equal the plain per-layer loop bit for bit (hops keep their per-receiver edge
+    order, the GEMMs are row-wise); parameter gradients are sums over all nodes taken in a different row order: 1e-5."""
+    import deformcontact_b200 as dc
+    from deformcontact_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    N, F, L = 40000, 32, 3
+    pos = torch.rand(N, 3, generator=gen).cuda()
+    x = torch.randn(N, 21, generator=gen).cuda()
+    gout = torch.randn(N, F, generator=gen).cuda()
+    ei = dc.knn_graph(pos, 8)
+    torch.manual_seed(0)
+    layers = torch.nn.ModuleList([getattr(dc, kind)(21 if i == 0 else F, F) for i in range(L)]).cuda()
+    res = []
+    for stacked in (False, True):
+        ops.clear_csr_cache()
+        layers.zero_grad()
+        xx = x.clone().requires_grad_(True)
+        assert ops.graph_csr(ei, N, "tag" if kind == "TAGConv" else "gcn", None).order is not None   # the relabelled path
+        if stacked:
+            n0 = dc._abi.lib().dc_launch_count()
+            y = dc.layer_stack(list(layers), xx, ei, relu=True)
+            n_stack = dc._abi.lib().dc_launch_count() - n0
+        else:
+            n0 = dc._abi.lib().dc_launch_count()
+            y = xx
+            for conv in layers:
+                y = conv(y, ei, relu=True)
+            n_loop = dc._abi.lib().dc_launch_count() - n0
+        y.backward(gout)
+        res.append(dict(y=y.detach().clone(), dx=xx.grad.clone(), dp=[p.grad.clone() for p in layers.parameters()]))
+    ops.clear_csr_cache()
+    assert n_stack < n_loop                       # 2 permutations instead of 2 per layer (and hop)
+    assert torch.equal(res[0]["y"], res[1]["y"])
+    assert torch.equal(res[0]["dx"], res[1]["dx"])
+    for a, b in zip(res[0]["dp"], res[1]["dp"]):
+        assert_close(a, b, what=f"{kind} stack parameter gradient")
+
+
 def test_encoder_branch_streams_do_not_change_a_bit(dc, monkeypatch):
     """model.BRANCH_STREAMS: the collider encoder branch on a second CUDA stream (forward, and through autograd's per-op streams
     backward) gives the same loss, prediction and gradients as the single-stream step, bit for bit, over several steps."""
