@@ -48,6 +48,7 @@ constexpr int T2_MAX_KPARTS = 64;   // weight gradients: 256 x 256 outputs over 
 // one problem of a batched launch (device table; the tensor maps are read by TMA straight from global memory)
 struct alignas(64) T2Problem {
   CUtensorMap mapA, mapB;
+  CUtensorMap mapC, mapE;   // TMA epilogue (T2Params::tepi): 32 x 32 fp32 boxes of the output and of the fused epilogue operand
   float* C;
   long long ldc;
   int M, N, kb_total, n_chunks;
@@ -77,6 +78,7 @@ struct T2Params {
   int raw_hi;             // 1: the MMA reads the raw fp32 tile as the hi operand (the tensor core ignores the low 13 bits); 0: masked copy
   int lo_rn;              // 1: lo = x - hi is pre-biased by half a tf32 ulp, so the tensor core's truncation rounds it to nearest
   float comp;             // per-MMA compensation of the accumulator's round-towards-zero bias (0 = off); see t2_numerics()
+  int tepi;               // 1: TMA epilogue (template TEPI): E tiles arrive by TMA while the tile's MMAs run, C tiles leave by TMA stores
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,6 +109,31 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+// the same two transfers with an L2 evict-first policy: tiles of matrices that stream through once (P / dS: 97 MB per group and head)
+// should not push the operand tiles every CTA re-reads out of L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, uint32_t src, int c0, int c1, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tensormap_acquire(const CUtensorMap* map) {
   asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(map) : "memory");
 }
@@ -197,6 +224,7 @@ struct T2Item {
   float* C;
   long long ldc;
   const CUtensorMap *mapA, *mapB;   // batched launches only
+  const CUtensorMap *mapC, *mapE;   // batched launches only (TMA epilogue)
   const float *E, *rowv;            // batched launches only: C = E o (acc - rowv[row])
   long long lde;
 };
@@ -217,6 +245,7 @@ __device__ __forceinline__ T2Item t2_item(const T2Params& p, int w, int& pidx, i
     it.kb1 = q->kb_total;
     it.M = q->M; it.N = q->N; it.C = q->C; it.ldc = q->ldc;
     it.mapA = &q->mapA; it.mapB = &q->mapB;
+    it.mapC = &q->mapC; it.mapE = &q->mapE;
     it.E = q->E; it.rowv = q->rowv; it.lde = q->lde;
     return it;
   }
@@ -228,35 +257,44 @@ __device__ __forceinline__ T2Item t2_item(const T2Params& p, int w, int& pidx, i
   it.kb1 = min(p.kb_total, it.kb0 + p.kb_per_part);
   it.M = p.M; it.N = p.N; it.C = p.C; it.ldc = p.ldc;
   it.mapA = nullptr; it.mapB = nullptr;
+  it.mapC = nullptr; it.mapE = nullptr;
   it.E = nullptr; it.rowv = nullptr; it.lde = 0;
   return it;
 }
 
-template <bool PAIR>
+template <bool PAIR, bool TEPI>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                 const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
-                const __grid_constant__ CUtensorMap mapB2, const __grid_constant__ CUtensorMap mapB3, const T2Params p) {
+                const __grid_constant__ CUtensorMap mapB2, const __grid_constant__ CUtensorMap mapB3,
+                const __grid_constant__ CUtensorMap mapC0, const T2Params p) {
+  static_assert(PAIR || !TEPI, "the TMA epilogue exists for CTA pairs only");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  float* epi_stage = reinterpret_cast<float*>(base_ptr + T2_STAGES * T2_STAGE_BYTES);
-  const uint32_t bar_base = base + T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOATS * 4;
-  // barriers (8 B each): full[3], xform[3], empty[3], tfull[2], tempty[2]; then the TMEM pointer
   // A CTA of a pair holds half a B tile: 48 KB per stage instead of 64, so the same 192 KB make FOUR stages — the hand-offs that
-  // cross the pair (split warps -> leader's MMA thread, MMA commit -> both producers) take a few hundred cycles longer
-  constexpr int NST = PAIR ? 4 : T2_STAGES;
+  // cross the pair (split warps -> leader's MMA thread, MMA commit -> both producers) take a few hundred cycles longer.
+  // TEPI: three stages (144 KB) and a 64 KB epilogue area instead of the 20 KB staging tiles: per epilogue warp one 32 x 64 block as
+  // two SWIZZLE_128B boxes of 32 x 32 floats — the landing zone of the fused epilogue operand AND the source of the TMA stores.
+  constexpr int NST = PAIR ? (TEPI ? 3 : 4) : T2_STAGES;
   constexpr int STB = PAIR ? 3 * T2_TILE_BYTES : T2_STAGE_BYTES;
+  constexpr int RING = NST * STB;
+  constexpr int EPI_WARP_BYTES = TEPI ? 8192 : T2_EPI_WARP_FLOATS * 4;
   constexpr int B_OFF = 2 * T2_TILE_BYTES;                              // B hi (raw) behind A hi (raw), A lo
   constexpr int BLO_OFF = PAIR ? B_OFF + T2_TILE_BYTES / 2 : B_OFF + T2_TILE_BYTES;   // B lo right behind B hi
-  static_assert(NST * STB == T2_STAGES * T2_STAGE_BYTES, "stage ring size");
+  static_assert(RING + 8 * EPI_WARP_BYTES + 256 + 1024 <= T2_SMEM_BYTES, "shared memory carve");
+  static_assert(TEPI || RING == T2_STAGES * T2_STAGE_BYTES, "stage ring size");
+  float* epi_stage = reinterpret_cast<float*>(base_ptr + RING);
+  const uint32_t bar_base = base + RING + 8 * EPI_WARP_BYTES;
+  // barriers (8 B each): full[4], xform[4], empty[4], tfull[2], tempty[2]; the TMEM pointer at +144; TEPI: ebar[8] at +160
+  auto ebar = [&](int slot) { return bar_base + 160u + 8u * slot; };
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto xform_bar = [&](int s) { return bar_base + 32u + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
   auto tfull_bar = [&](int j) { return bar_base + 96u + 8u * j; };
   auto tempty_bar = [&](int j) { return bar_base + 112u + 8u * j; };
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + T2_STAGES * T2_STAGE_BYTES + 8 * T2_EPI_WARP_FLOATS * 4 + 144);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + RING + 8 * EPI_WARP_BYTES + 144);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // PAIR: the two CTAs of a cluster own row tiles 2 q and 2 q + 1 and HALF of the B tile each (64 of its 128 rows); CTA 0 (the
@@ -278,6 +316,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       mbar_init(tfull_bar(j), 1);
       mbar_init(tempty_bar(j), PAIR ? 16 : 256);   // PAIR: one arrival per epilogue warp of both CTAs
     }
+    if (TEPI)
+      for (int sl = 0; sl < 8; ++sl) mbar_init(ebar(sl), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -461,6 +501,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     float* stg = epi_stage + ((half * 4) + q) * T2_EPI_WARP_FLOATS;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
     int chain = 0, pidx = 0;
+    // TEPI: this warp's 32 x 64 block lives in two SWIZZLE_128B boxes (32 rows x 32 floats, 4 KB each): row r at r * 128 B, its
+    // 16-byte chunk c at physical chunk c ^ (r & 7) — the 8 lanes of a quarter-warp touch 8 different chunks: conflict-free
+    const int slot = half * 4 + q;
+    const uint32_t ebuf = base + RING + slot * 8192;
+    uint8_t* ebuf_ptr = base_ptr + RING + slot * 8192;
+    uint32_t eph = 0;
+    int efenced = -1;
+    const bool ehint = TEPI && (p.tepi & 2);
+    const uint64_t epol = ehint ? l2_evict_first_policy() : 0ull;
     for (int w = w0; w < p.items; w += wstep) {
       const T2Item item = t2_item(p, w, pidx, rank);
       const bool vec_ok = ((item.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(item.C) & 15) == 0) &&
@@ -468,7 +517,32 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       float acc[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-      if (item.E != nullptr) {
+      const CUtensorMap* mC = TEPI ? (p.batch ? item.mapC : &mapC0) : nullptr;
+      const int ecol0 = item.n0 + half * 64, erow0 = item.m0 + q * 32;
+      if (TEPI) {
+        // The previous item's stores have read the block; then the fused epilogue operand of THIS item starts its way into it
+        // while the tile's MMAs are still running: no load latency is left on the epilogue's critical path.
+        if (lane == 0) {
+          bulk_wait_read0();
+          if (p.batch && efenced != pidx) {
+            tensormap_acquire(item.mapC);
+            if (item.E != nullptr) tensormap_acquire(item.mapE);
+            efenced = pidx;
+          }
+          if (item.E != nullptr) {
+            mbar_expect_tx(ebar(slot), 8192);
+            if (ehint) {
+              tma_load_2d_hint(ebuf, item.mapE, ebar(slot), ecol0, erow0, epol);
+              tma_load_2d_hint(ebuf + 4096, item.mapE, ebar(slot), ecol0 + 32, erow0, epol);
+            } else {
+              tma_load_2d(ebuf, item.mapE, ebar(slot), ecol0, erow0);
+              tma_load_2d(ebuf + 4096, item.mapE, ebar(slot), ecol0 + 32, erow0);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (!TEPI && item.E != nullptr) {
         // The fused epilogue operand of a 32 x 64 block (2-3 lines per row) is pulled into L2 ONE ITEM AHEAD: with the fused
         // epilogue this warp is the bottleneck of the tile pipeline (the MMAs of its current item are long done when it gets
         // here), so a prefetch for the current item would be issued just before its first use.
@@ -517,6 +591,58 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             for (int i = 0; i < 32; ++i) acc[(part & 1) * 32 + i] += __uint_as_float(r[i]);
           }
         }
+      }
+      if (TEPI) {
+        // ---- registers -> (o E) -> swizzled block -> TMA stores (rows / columns beyond M / N are clipped by the TMA unit; the
+        // operand's out-of-range elements arrive as zeros)
+        const int row = erow0 + lane;
+        float d = 0.f;
+        if (item.E != nullptr) {
+          if (row < item.M) d = __ldg(item.rowv + row);
+          mbar_wait(ebar(slot), eph);
+          eph ^= 1;
+        }
+        const float* bias = p.bias;
+        const bool bias_vec = bias && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4* cell = reinterpret_cast<float4*>(ebuf_ptr + b * 4096 + lane * 128 + ((c ^ (lane & 7)) << 4));
+            float4 v = make_float4(acc[b * 32 + c * 4], acc[b * 32 + c * 4 + 1], acc[b * 32 + c * 4 + 2], acc[b * 32 + c * 4 + 3]);
+            if (bias) {
+              const int col = ecol0 + b * 32 + c * 4;
+              if (bias_vec && col + 3 < item.N) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              } else {
+                if (col < item.N) v.x += __ldg(bias + col);
+                if (col + 1 < item.N) v.y += __ldg(bias + col + 1);
+                if (col + 2 < item.N) v.z += __ldg(bias + col + 2);
+                if (col + 3 < item.N) v.w += __ldg(bias + col + 3);
+              }
+            }
+            if (item.E != nullptr) {   // fused softmax backward  dS = P o (dP - rowsum(dP o P))  (E = P, rowv = rowdot(dO, O))
+              const float4 e = *cell;
+              v.x = e.x * (v.x - d); v.y = e.y * (v.y - d); v.z = e.z * (v.z - d); v.w = e.w * (v.w - d);
+            }
+            if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            *cell = v;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (ehint) {
+            tma_store_2d_hint(mC, ebuf, ecol0, erow0, epol);
+            tma_store_2d_hint(mC, ebuf + 4096, ecol0 + 32, erow0, epol);
+          } else {
+            tma_store_2d(mC, ebuf, ecol0, erow0);
+            tma_store_2d(mC, ebuf + 4096, ecol0 + 32, erow0);
+          }
+          bulk_commit();
+        }
+        continue;
       }
       // ---- write the 32 x 64 block of this warp, 16 columns at a time through a padded staging tile
       const bool to_slab = p.k_parts > 1;
@@ -627,6 +753,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     }
   }
 
+  if (TEPI && warp >= 4 && !(warp >= 8 && warp < 12) && lane == 0) bulk_wait0();   // this warp's last TMA stores have left the block
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: neither CTA may leave while the other can still signal its barriers
   if (warp == 2) {
@@ -731,16 +858,33 @@ int t2_pair() {
   return pair;
 }
 
+// TMA epilogue (CTA pairs only): DCB200_T2_TEPI = 0 off, 1 (default) for short contractions (K <= 512: the products whose tile
+// time is set by the epilogue — attention scores, the fused softmax-backward product, the K = 256 layer products), 2 for every K
+int t2_tepi_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("DCB200_T2_TEPI");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode;
+}
+bool t2_tepi_ok(int pair, int64_t kb_max, int k_parts, int accumulate) {
+  const int mode = t2_tepi_mode();
+  return pair && mode > 0 && k_parts == 1 && !accumulate && (mode > 1 || kb_max <= T2_SHORT_KB);
+}
+bool t2_tepi_operand_ok(const float* ptr, int64_t ld) { return ptr && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
+
 // one persistent CTA per SM; PAIR: clusters of two CTAs (an even grid)
-int t2_launch(const CUtensorMap* mA, const CUtensorMap* mB, const T2Params& p, cudaStream_t st) {
+int t2_launch(const CUtensorMap* mA, const CUtensorMap* mB, const CUtensorMap& mC, const T2Params& p, cudaStream_t st) {
   static DeviceOnce attr_set;
   if (attr_set.first()) {
-    DC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
-    DC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    DC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    DC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    DC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
   }
   if (!p.pair) {
     const int grid = p.items < sm_count() ? p.items : sm_count();
-    gemm_tc2_kernel<false><<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(mA[0], mA[1], mA[2], mA[3], mB[0], mB[1], mB[2], mB[3], p);
+    gemm_tc2_kernel<false, false><<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(mA[0], mA[1], mA[2], mA[3], mB[0], mB[1], mB[2], mB[3], mC, p);
   } else {
     const int pairs = p.items < sm_count() / 2 ? p.items : sm_count() / 2;
     cudaLaunchConfig_t cfg{};
@@ -753,7 +897,8 @@ int t2_launch(const CUtensorMap* mA, const CUtensorMap* mB, const T2Params& p, c
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    DC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<true>, mA[0], mA[1], mA[2], mA[3], mB[0], mB[1], mB[2], mB[3], p));
+    if (p.tepi) DC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<true, true>, mA[0], mA[1], mA[2], mA[3], mB[0], mB[1], mB[2], mB[3], mC, p));
+    else DC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<true, false>, mA[0], mA[1], mA[2], mA[3], mB[0], mB[1], mB[2], mB[3], mC, p));
   }
   DC_LAUNCH_CHECK();
   return DC_OK;
@@ -833,7 +978,11 @@ int gemm_tc2(const dc_gemm_seg* segs, int nseg, int transA, int transB, int64_t 
     DC_REQUIRE(workspace && workspace_bytes >= need, DC_EWORKSPACE, "gemm_tc2: workspace %zu < %zu", workspace_bytes, need);
     p.partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   }
-  if (int rc = t2_launch(mA, mB, p, st)) return rc;
+  CUtensorMap mC{};
+  p.tepi = t2_tepi_ok(p.pair, p.kb_total, p.k_parts, accumulate) && t2_tepi_operand_ok(C, ldc);
+  if (p.tepi)
+    if (int rc = make_map2(&mC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  if (int rc = t2_launch(mA, mB, mC, p, st)) return rc;
   if (p.k_parts > 1) {
     const long long MN = (long long)M * N;
     t2_reduce_kernel<<<(unsigned)cdiv(MN, 256), 256, 0, st>>>(p.partial, p.k_parts, MN, (int)N, C, ldc, bias, relu, accumulate);
@@ -876,6 +1025,16 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
   const uint32_t b_box_rows = pair ? T2_BN / 2 : T2_BN;
   int64_t items = 0;
   int64_t max_kb = 0;
+  // TMA epilogue: every problem's output (and epilogue operand) must be addressable by a tensor map
+  int64_t kb_all = 0;
+  bool tepi_operands = true;
+  for (int i = 0; i < count; ++i) {
+    const dc_gemm_problem& q = probs[i];
+    if (q.M <= 0 || q.N <= 0) continue;
+    if (cdiv(q.K, T2_BK) > kb_all) kb_all = cdiv(q.K, T2_BK);
+    if (!t2_tepi_operand_ok(q.C, q.ldc) || (q.E && !t2_tepi_operand_ok(q.E, q.lde))) tepi_operands = false;
+  }
+  const int tepi = t2_tepi_ok(pair, kb_all, 1, accumulate) && tepi_operands;
   for (int i = 0; i < count; ++i) {
     const dc_gemm_problem& q = probs[i];
     DC_REQUIRE(q.M >= 0 && q.N >= 0 && q.K >= 0, DC_EINVAL, "gemm_batched: negative size in problem %d", i);
@@ -900,6 +1059,11 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
     t.C = q.C; t.ldc = q.ldc; t.M = (int)q.M; t.N = (int)q.N;
     t.E = q.E; t.rowv = q.rowv; t.lde = q.lde;
     DC_REQUIRE(!q.E || (q.rowv && q.lde >= q.N), DC_EINVAL, "gemm_batched: problem %d: epilogue operand needs rowv and lde >= N", i);
+    if (tepi) {
+      if (int rc = make_map2(&t.mapC, q.C, (uint64_t)q.N, (uint64_t)q.M, (uint64_t)q.ldc, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+      if (q.E)
+        if (int rc = make_map2(&t.mapE, q.E, (uint64_t)q.N, (uint64_t)q.M, (uint64_t)q.lde, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    }
     t.kb_total = (int)cdiv(q.K, T2_BK);
     if (t.kb_total > max_kb) max_kb = t.kb_total;
     t.n_chunks = (int)cdiv(q.N, T2_BN);
@@ -926,8 +1090,12 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
   p.raw_hi = 1;
   if (const char* e = getenv("DCB200_T2_RAWHI")) p.raw_hi = e[0] == '1';
   t2_numerics(p);
+  // batched products write matrices far larger than L2 that the next kernel reads from the start again: evict-first (DCB200_T2_TEPI_HINT=0: off)
+  static int hint = -1;
+  if (hint < 0) { const char* e = getenv("DCB200_T2_TEPI_HINT"); hint = e ? atoi(e) : 1; }
+  p.tepi = tepi ? (hint ? 3 : 1) : 0;
   CUtensorMap dummy[4]{};
-  return t2_launch(dummy, dummy, p, st);
+  return t2_launch(dummy, dummy, dummy[0], p, st);
 }
 
 }  // namespace dcb

@@ -110,7 +110,7 @@ class GraphNet(nn.Module):
         drop = (lambda t: F.dropout(t, p=self.dropout_rate, training=self.training)) if self.dropout_rate > 0 else None
 
         def branch(convs, graph, ptr):
-            return layer_stack(list(convs), graph.x, graph.edge_index, relu=True, ptr=ptr, between=drop)
+            return layers.layer_stack(list(convs), graph.x, graph.edge_index, relu=True, ptr=ptr, between=drop)
 
         if BRANCH_STREAMS and graph_rigid.x.is_cuda:
             # The two encoder branches are independent until the attention.  The collider branch is small (762-node graphs): on

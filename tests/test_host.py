@@ -296,3 +296,32 @@ def test_attention_groups_partition_the_batch():
     assert g == [(0, 25, 0, 6), (25, 40, 6, 12), (40, 60, 12, 15)]
     assert attention._groups(ptr_s, ptr_r, None) == [(0, 60, 0, 15)]
     assert sum(s1 - s0 for s0, s1, _, _ in g) == ptr_s[-1] and sum(r1 - r0 for _, _, r0, r1 in g) == ptr_r[-1]
+
+
+def test_product_modules_have_no_undefined_names():
+    """The product path cannot run here (no GPU, no CPU fallback), so a missing import would only surface on the GPU box:
+    every name a function body loads must be bound in its module, its enclosing scopes or builtins (symtable walk)."""
+    import builtins, glob, os, symtable
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    files = glob.glob(os.path.join(root, "deformcontact_b200", "*.py")) + [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]
+    bad = []
+    for f in files:
+        top = symtable.symtable(open(f).read(), f, "exec")
+        module_names = {s.get_name() for s in top.get_symbols() if s.is_assigned() or s.is_imported() or s.is_namespace()}
+
+        def walk(tab):
+            for s in tab.get_symbols():
+                if s.is_global() and s.is_referenced() and not s.is_assigned():
+                    n = s.get_name()
+                    if n not in module_names and not hasattr(builtins, n) and n not in ("__file__", "__name__", "__doc__"):
+                        bad.append((os.path.basename(f), tab.get_name(), n))
+            for c in tab.get_children():
+                walk(c)
+        for c in top.get_children():
+            walk(c)
+        for s in top.get_symbols():   # module level: referenced but never bound
+            n = s.get_name()
+            if s.is_referenced() and not (s.is_assigned() or s.is_imported() or s.is_namespace()) and not hasattr(builtins, n) \
+                    and n not in ("__file__", "__name__", "__doc__"):
+                bad.append((os.path.basename(f), "<module>", n))
+    assert not bad, bad
