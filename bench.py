@@ -677,6 +677,8 @@ def run_infer_c2(args, emit=True):
     ms = _ev_time(step, args.steps, max(args.warmup, 3))
     launches = (lib.dc_launch_count() - l0) // (args.steps + max(args.warmup, 3))
     enc_ms = _ev_time(enc, args.steps, max(args.warmup, 3))
+    # the kNN-k edge construction of the same batch (utils/pointcloud_utils.py:7-13 per sample): batched tiled brute force (K4)
+    knn_ms = _ev_median(lambda: dc.knn_graph(rest.pos, args.k, ptr=rest.ptr), 7)
     # end-to-end: raw per-sample inputs in pinned host memory -> H2D -> batch assembly on the GPU (N3) -> model -> predicted
     # positions read back (eval.py:107-111 plus the D2H a caller needs to use the result)
     eptr_l = (rest._edge_ptr if rest._edge_ptr is not None else
@@ -705,6 +707,7 @@ def run_infer_c2(args, emit=True):
             "config": {"workload": f"C2 everyday.json inference, {B} graphs x {n} nodes kNN-{args.k} + colliders",
                        "attention": f"groups of {args.attn_group}", "l2": "inputs larger than L2"},
             "clocks": clocks, "gpu_launches": int(launches), "encoder_only_ms": enc_ms,
+            "knn_build_ms": knn_ms, "knn_pair_distances_per_sec": B * float(n) * n / (knn_ms * 1e-3),
             "e2e": {"value": B / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": pos_host.numel() * 4, "result_equals_resident": ok},
             "encoder_edge_traversals_per_sec": 6 * E / (enc_ms * 1e-3)}
