@@ -195,3 +195,56 @@ def test_fused_losses(dc):
         assert_close_arbiter(a, b32, b64, what=f"fused loss {name}")
     again = run(torch.float32, "cuda", True)
     assert all(torch.equal(x, y) for x, y in zip(ours, again)), "deterministic"
+
+
+def test_gemm_tma_epilogue_equals_the_staged_epilogue_bit_for_bit(dc):
+    """K2 TMA epilogue (gemm_tc2.cu, template TEPI: contractions K <= 512 of CTA pairs without accumulate) against the staged
+    epilogue on the same products, in process: (a) a batch of short-K problems runs with TMA epilogues; the same problems
+    followed by ONE long-K problem send the whole launch down the staged path; (b) a single product with bias + ReLU against
+    the same product accumulated onto zeros (accumulate disables the TMA epilogue).  Ragged M / N (clipped TMA boxes), odd row
+    tile counts (the pair's missing tile), every layout, plain and fused (C = E o (acc - rowv)) epilogues."""
+    from deformcontact_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(9)
+    rn = lambda *s: torch.randn(*s, generator=g, device="cuda")
+    shapes = [(300, 520, 256), (129, 36, 64), (1000, 3048, 32), (31, 4, 512), (257, 100, 96)]
+    for ta in (False, True):
+        for tb in (False, True):
+            for fused in (False, True):
+                if fused and (ta or not tb):
+                    continue
+                def build():
+                    probs = []
+                    gg = torch.Generator(device="cuda").manual_seed(10)
+                    for M, N, K in shapes:
+                        Mp, Np = (M + 3) // 4 * 4, (N + 3) // 4 * 4
+                        A = torch.randn((K, Mp) if ta else (M, K), generator=gg, device="cuda")[:, :M if ta else K]
+                        B = torch.randn((N, K) if tb else (K, Np), generator=gg, device="cuda")[:, :K if tb else N]
+                        Cm = torch.full((M, Np), -7.0, device="cuda")[:, :N]          # row pitch % 4 == 0 (TMA), N itself ragged
+                        if fused:
+                            E = torch.rand((M, Np), generator=gg, device="cuda")[:, :N]
+                            probs.append((A, B, Cm, E, torch.randn(M, generator=gg, device="cuda")))
+                        else:
+                            probs.append((A, B, Cm))
+                    return probs
+                tma = build()
+                ops.gemm_batched(tma, trans_a=ta, trans_b=tb)
+                staged = build()
+                Kl = 1024
+                Al = rn(Kl, 64) if ta else rn(64, Kl)
+                Bl = rn(64, Kl) if tb else rn(Kl, 64)
+                long_problem = (Al, Bl, torch.empty(64, 64, device="cuda")) + ((torch.rand(64, 64, device="cuda"), rn(64)) if fused else ())
+                ops.gemm_batched(staged + [long_problem], trans_a=ta, trans_b=tb)
+                for i, (p, q) in enumerate(zip(tma, staged)):
+                    assert torch.equal(p[2], q[2]), (ta, tb, fused, shapes[i])
+                    if fused:
+                        ref = p[3].double() * ((p[0].double() @ p[1].double().T) - p[4].double()[:, None])
+                        assert_close(p[2], ref.float(), what=f"fused TMA epilogue {shapes[i]}")
+    for M, N, K in [(300, 520, 256), (129, 36, 64), (4000, 256, 256)]:
+        A, B, b = rn(M, K), rn(N, K), rn(N)
+        for relu in (False, True):
+            out_tma = ops.gemm([(A, B)], M, N, bias=b, relu=relu, precision=dc._abi.GEMM_TF32X3)
+            out_staged = ops.gemm([(A, B)], M, N, bias=b, relu=relu, out=torch.zeros(M, N, device="cuda"), accumulate=True,
+                                  precision=dc._abi.GEMM_TF32X3)
+            assert torch.equal(out_tma, out_staged), (M, N, K, relu)
+            ref = A.double() @ B.double().T + b.double()
+            assert_close(out_tma, (ref.relu() if relu else ref).float(), what="TMA epilogue bias / relu")
