@@ -305,6 +305,14 @@ DC_API int dc_knn_grid(const float* pos, int64_t num_points, int32_t k, int loop
                 void* workspace, size_t workspace_bytes, dc_stream_t stream);
 DC_API int dc_radius_grid(const float* pos, int64_t num_points, float r, int32_t max_nbr, int loop, int32_t* nbr_out,
                    int32_t* count_out, int32_t* order_out, void* workspace, size_t workspace_bytes, dc_stream_t stream);
+/* K4g, batched (kNN): one grid per graph of a batch of large clouds (`ptr` as in dc_knn: torch_cluster.knn_graph with a `batch`
+ * vector, utils/pointcloud_utils.py:10 applied per sample) in the same launches: per-graph bounding box and cell size, the graphs'
+ * cells end to end in one cell array, one counting sort, every query walks its own graph's grid.  Bit-identical to dc_knn; worth
+ * it from about a thousand points per graph (short brute-force scans spend their time in the top-k insertion path).  One
+ * device-side decision for the whole batch: if the grids cannot split the clouds the brute-force kernel runs instead. */
+DC_API size_t dc_knn_grid_batched_workspace_bytes(int64_t num_points, int64_t num_graphs);
+DC_API int dc_knn_grid_batched(const float* pos, const int64_t* ptr, int64_t num_graphs, int64_t num_points, int32_t k, int loop,
+                        int32_t* nbr_out, void* workspace, size_t workspace_bytes, dc_stream_t stream);
 /* order[i] = index of the i-th point in grid-cell order (the counting sort of K4g): a spatially coherent relabelling
  * of a large point cloud.  A permutation of 0..N-1; the order inside a cell is unspecified.  Workspace as dc_knn_grid. */
 DC_API int dc_cell_order(const float* pos, int64_t num_points, int32_t* order, void* workspace, size_t workspace_bytes,

@@ -513,8 +513,64 @@ def test_grid_search_large_cloud_vs_oracle_and_auto_dispatch(dc):
     want = idx[:, :16].sort(1).values
     tab = ei[0].cpu().reshape(40000, 16)[sub].sort(1).values
     assert clean.sum() >= sub.numel() - 2 and torch.equal(tab[clean], want[clean])
-    # batched clouds never take the grid path
+    # a batch vector is never taken for one cloud (batches of large clouds have their own grid-per-graph entry point)
     assert not ops._use_grid(40000, torch.zeros(40000, dtype=torch.long), None, 17)
+
+
+def test_batched_grid_search_bit_identical_to_brute_force(dc):
+    """dc_knn_grid_batched (one grid per graph of a batch) == dc_knn (tiled brute force) bit for bit, incl. neighbour order:
+    a ragged batch of uniform / clustered / degenerate clouds with an empty graph, a one-point graph and a graph with fewer
+    than k points in between; several k, loop on / off; through ``ptr`` and through a ``batch`` vector; auto dispatch by the
+    average cloud size; the device-side hand-back of a batch a grid cannot split."""
+    from deformcontact_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    clouds = _clouds()
+    tiny = [torch.zeros(0, 3), torch.rand(1, 3, generator=g), torch.rand(5, 3, generator=g)]
+    stretched = torch.rand(3000, 3, generator=g) * torch.tensor([10.0, 0.1, 1.0])
+    # "benign": grids split every cloud (the device-side cost estimate keeps the batch on the grid); "mixed": clustered / planar /
+    # stretched clouds as well — whichever kernel the device-side decision picks, the table is the brute-force one
+    benign = [clouds["uniform"], tiny[0], clouds["duplicates"], tiny[1], clouds["lattice"], tiny[2], clouds["shifted"],
+              clouds["coincident"], torch.rand(5000, 3, generator=g) - 2.0]
+    mixed = [clouds["uniform"], tiny[0], clouds["clustered"], tiny[1], clouds["duplicates"], tiny[2], clouds["planar"],
+             clouds["lattice"], clouds["coincident"], clouds["shifted"], stretched]
+    try:
+        for parts, want_grid in ((benign, True), (mixed, None)):
+            sizes = [p.shape[0] for p in parts]
+            pos = torch.cat(parts).cuda()
+            ptr = torch.tensor([0] + sizes).cumsum(0).cuda()
+            batch = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes)).cuda()
+            for k, loop in ((8, False), (16, True), (40, False), (100, False)):
+                ops.KNN_MODE = "brute"
+                ref = ops.knn_table(pos, k, ptr=ptr, loop=loop)
+                ops.KNN_MODE = "grid"
+                out = ops.knn_table(pos, k, ptr=ptr, loop=loop)
+                assert torch.equal(out, ref), f"batched knn k={k} loop={loop}: {(out != ref).sum().item()} entries differ"
+                if want_grid is not None:
+                    assert ops.grid_took_it(out) == want_grid
+                assert torch.equal(ops.knn_table(pos, k, batch=batch, loop=loop), ref)
+        # neighbours never cross graph boundaries
+        gid = batch[out.clamp(min=0).long()]
+        assert bool(((gid == batch[:, None]) | (out < 0)).all())
+        # auto: by the total and the average cloud size
+        ops.KNN_MODE = "auto"
+        big = torch.rand(8 * 3000, 3, generator=g).cuda()
+        p4 = torch.arange(0, 8 * 3000 + 1, 3000).cuda()
+        assert ops.grid_took_it(ops.knn_table(big, 8, ptr=p4))
+        small = torch.arange(0, 8 * 3000 + 1, 120).cuda()
+        t_small = ops.knn_table(big, 8, ptr=small)
+        assert not ops.grid_took_it(t_small)
+        assert not ops.grid_took_it(ops.knn_table(big[:6000], 8, ptr=p4[:3]))      # a small batch stays on the brute-force kernel
+        ops.KNN_MODE = "grid"
+        assert torch.equal(ops.knn_table(big, 8, ptr=small), t_small)
+        # one graph with a far outlier: its grid is one cell -> the whole batch goes back to the brute-force kernel, same output
+        bad = big.clone()
+        bad[5] = 1.0e4
+        out = ops.knn_table(bad, 8, ptr=p4)
+        ops.KNN_MODE = "brute"
+        assert torch.equal(out, ops.knn_table(bad, 8, ptr=p4))
+        assert not ops.grid_took_it(out)
+    finally:
+        ops.KNN_MODE = "auto"
 
 
 def test_grid_search_hands_unsplittable_clouds_to_brute_force(dc):
