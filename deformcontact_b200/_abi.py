@@ -77,6 +77,7 @@ PROTOTYPES = {
     "dc_knn_grid": (_int, [_p, _i64, _i32, _int, _p, _p, _p, _sz, _p]),
     "dc_knn_grid_batched_workspace_bytes": (_sz, [_i64, _i64]),
     "dc_knn_grid_batched": (_int, [_p, _p, _i64, _i64, _i32, _int, _p, _p, _sz, _p]),
+    "dc_radius_grid_batched": (_int, [_p, _p, _i64, _i64, _f32, _i32, _int, _p, _p, _p, _sz, _p]),
     "dc_radius_grid": (_int, [_p, _i64, _f32, _i32, _int, _p, _p, _p, _p, _sz, _p]),
     "dc_cell_order": (_int, [_p, _i64, _p, _p, _sz, _p]),
     "dc_permute_rows": (_int, [_p, _i64, _p, _p, _i64, _i64, _i32, _p]),

@@ -454,6 +454,28 @@ extern "C" int dc_knn_grid_batched(const float* pos, const int64_t* ptr, int64_t
   return launch_knn_brute(pos, ptr, B, N, kk, loop, nbr_out, &g.gp->use_grid, st);   // runs iff the batch was handed back (use_grid == 0)
 }
 
+extern "C" int dc_radius_grid_batched(const float* pos, const int64_t* ptr, int64_t B, int64_t N, float r, int32_t max_nbr, int loop,
+                                      int32_t* nbr_out, int32_t* count_out, void* workspace, size_t workspace_bytes,
+                                      dc_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DC_REQUIRE(N >= 0 && B >= 1 && max_nbr >= 1, DC_EINVAL, "radius_grid_batched: bad sizes");
+  if (N == 0) return DC_OK;
+  DC_REQUIRE(pos && ptr && nbr_out && workspace, DC_EINVAL, "radius_grid_batched: null pointer");
+  DC_REQUIRE(N < (1ll << 31) && B < (1ll << 24) && batched_total_cells(N, B) < (1ll << 31), DC_ENOSUP, "radius_grid_batched: batch too large");
+  const int cap = max_nbr + (loop ? 0 : 1);
+  DC_REQUIRE(cap <= 128, DC_ENOSUP, "radius_grid_batched: max_num_neighbors=%d exceeds the supported maximum (127)", max_nbr);
+  const GridWs g = carve_grid(workspace, N, B > 1 ? B : 2);
+  DC_REQUIRE(workspace_bytes >= g.bytes, DC_EWORKSPACE, "radius_grid_batched: workspace too small");
+  if (int rc = build_grid_batched(pos, ptr, B, N, g, st)) return rc;
+  const float r2 = r * r;  // fp32 product, as torch_cluster / dc_radius
+  const unsigned grid = (unsigned)cdiv(N, GRID_THREADS / 32);
+  if (cap <= 32) grid_search_kernel<1, 1><<<grid, GRID_THREADS, 0, st>>>(g.sorted, g.count, g.gp, N, cap, loop, cap, r2, nbr_out, count_out, ptr, (int)B);
+  else if (cap <= 64) grid_search_kernel<2, 1><<<grid, GRID_THREADS, 0, st>>>(g.sorted, g.count, g.gp, N, cap, loop, cap, r2, nbr_out, count_out, ptr, (int)B);
+  else grid_search_kernel<4, 1><<<grid, GRID_THREADS, 0, st>>>(g.sorted, g.count, g.gp, N, cap, loop, cap, r2, nbr_out, count_out, ptr, (int)B);
+  DC_LAUNCH_CHECK();
+  return launch_radius_brute(pos, ptr, B, N, r2, cap, loop, nbr_out, count_out, &g.gp->use_grid, st);
+}
+
 extern "C" int dc_radius_grid(const float* pos, int64_t N, float r, int32_t max_nbr, int loop, int32_t* nbr_out,
                               int32_t* count_out, int32_t* order_out, void* workspace, size_t workspace_bytes, dc_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;

@@ -804,17 +804,25 @@ def _ptr_tensor(num_points, batch, ptr, device):
     return torch.cat([counts.new_zeros(1), counts.cumsum(0)]).to(_i64)
 
 
-# Neighbour search strategy: "auto" = uniform grid (K4g) for a single point cloud of at least KNN_GRID_MIN points and — kNN only —
+# Neighbour search strategy: "auto" = uniform grid (K4g) for a single point cloud of at least KNN_GRID_MIN points and
 # one grid per graph for a batch of at least KNN_GRID_MIN points whose clouds average at least KNN_GRID_BATCH_MIN (dc_knn_grid_batched), tiled brute force
-# (K4) otherwise; "brute" / "grid" force one (radius search on a grid needs batch=None).  Results are bit-identical.
+# (K4) otherwise; "brute" / "grid" force one.  Results are bit-identical.
 KNN_MODE = os.environ.get("DCB200_KNN", "auto")
 KNN_GRID_MIN = 16384
+RADIUS_GRID_BATCH_MIN = 1024   # the radius scan has no insertion path: its brute-force form holds out until ~1000 points per graph
 KNN_GRID_BATCH_MIN = int(os.environ.get("DCB200_KNN_GRID_BATCH_MIN", "256"))   # measured: 2x faster than brute force from 250 points per graph up
 
 
 def _use_grid(N, batch, ptr, width):
     single = batch is None and (ptr is None or ptr.numel() == 2)
     return single and width <= 128 and (KNN_MODE == "grid" or (KNN_MODE == "auto" and N >= KNN_GRID_MIN))
+
+
+def _use_grid_batched(N, B, width, per_graph_min=None):
+    """One grid per graph (dc_knn_grid_batched / dc_radius_grid_batched) for a batch of B >= 2 clouds."""
+    per_graph_min = KNN_GRID_BATCH_MIN if per_graph_min is None else per_graph_min
+    return (B >= 2 and width <= 128 and B < (1 << 24)
+            and (KNN_MODE == "grid" or (KNN_MODE == "auto" and N >= KNN_GRID_MIN and N >= B * per_graph_min)))
 
 
 def knn_table(pos, k, batch=None, ptr=None, loop=False):
@@ -834,7 +842,7 @@ def knn_table(pos, k, batch=None, ptr=None, loop=False):
         return tab
     p = _ptr_tensor(N, batch, ptr, pos.device)
     B = p.numel() - 1
-    if B >= 2 and W <= 128 and B < (1 << 24) and (KNN_MODE == "grid" or (KNN_MODE == "auto" and N >= KNN_GRID_MIN and N >= B * KNN_GRID_BATCH_MIN)):
+    if _use_grid_batched(N, B, W):
         nb = _abi.lib().dc_knn_grid_batched_workspace_bytes(N, B)
         ws = _workspace(nb, pos.device)
         _abi.call("dc_knn_grid_batched", _ptr(pos), _ptr(p), B, N, k, int(bool(loop)), _ptr(tab), _ptr(ws), nb, _stream())
@@ -860,8 +868,15 @@ def radius_table(pos, r, batch=None, ptr=None, loop=False, max_num_neighbors=32)
         tab._cell_order = order
         return tab, cnt
     p = _ptr_tensor(N, batch, ptr, pos.device)
-    _abi.call("dc_radius", _ptr(pos), _ptr(p), p.numel() - 1, N, float(r), max_num_neighbors, int(bool(loop)), _ptr(tab),
-              _ptr(cnt), _stream())
+    B = p.numel() - 1
+    if _use_grid_batched(N, B, W, RADIUS_GRID_BATCH_MIN):
+        nb = _abi.lib().dc_knn_grid_batched_workspace_bytes(N, B)
+        ws = _workspace(nb, pos.device)
+        _abi.call("dc_radius_grid_batched", _ptr(pos), _ptr(p), B, N, float(r), max_num_neighbors, int(bool(loop)), _ptr(tab), _ptr(cnt),
+                  _ptr(ws), nb, _stream())
+        tab._grid_ws = ws
+        return tab, cnt
+    _abi.call("dc_radius", _ptr(pos), _ptr(p), B, N, float(r), max_num_neighbors, int(bool(loop)), _ptr(tab), _ptr(cnt), _stream())
     return tab, cnt
 
 

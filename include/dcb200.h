@@ -313,6 +313,11 @@ DC_API int dc_radius_grid(const float* pos, int64_t num_points, float r, int32_t
 DC_API size_t dc_knn_grid_batched_workspace_bytes(int64_t num_points, int64_t num_graphs);
 DC_API int dc_knn_grid_batched(const float* pos, const int64_t* ptr, int64_t num_graphs, int64_t num_points, int32_t k, int loop,
                         int32_t* nbr_out, void* workspace, size_t workspace_bytes, dc_stream_t stream);
+/* ... and torch_cluster.radius_graph with a `batch` vector on the same per-graph grids (workspace as dc_knn_grid_batched);
+ * bit-identical to dc_radius. */
+DC_API int dc_radius_grid_batched(const float* pos, const int64_t* ptr, int64_t num_graphs, int64_t num_points, float r,
+                           int32_t max_nbr, int loop, int32_t* nbr_out, int32_t* count_out, void* workspace,
+                           size_t workspace_bytes, dc_stream_t stream);
 /* order[i] = index of the i-th point in grid-cell order (the counting sort of K4g): a spatially coherent relabelling
  * of a large point cloud.  A permutation of 0..N-1; the order inside a cell is unspecified.  Workspace as dc_knn_grid. */
 DC_API int dc_cell_order(const float* pos, int64_t num_points, int32_t* order, void* workspace, size_t workspace_bytes,

@@ -22,4 +22,11 @@ for B, n in ((64, 5000), (256, 2000), (512, 1000), (1024, 500), (2048, 250), (16
         res[mode] = (t(lambda: ops.knn_table(pos, 8, ptr=ptr)), ops.knn_table(pos, 8, ptr=ptr))
     ops.KNN_MODE = "auto"
     same = torch.equal(res["brute"][1], res["grid"][1])
+    rr = (3.0 * 8 / (4.0 * 3.141592653589793 * n)) ** (1.0 / 3.0)   # ~8 neighbours per point
+    rad = {}
+    for mode in ("brute", "grid"):
+        ops.KNN_MODE = mode
+        rad[mode] = (t(lambda: ops.radius_table(pos, rr, ptr=ptr)), ops.radius_table(pos, rr, ptr=ptr)[0])
+    ops.KNN_MODE = "auto"
+    print(f"{B} x {n}: radius (r for ~8 hits, max 32) brute {rad['brute'][0]:.3f} ms, grid per graph {rad['grid'][0]:.3f} ms, identical {torch.equal(rad['brute'][1], rad['grid'][1])}")
     print(f"{B} x {n}: brute {res['brute'][0]:.3f} ms, grid per graph {res['grid'][0]:.3f} ms (took the grid: {ops.grid_took_it(res['grid'][1])}), identical {same}")

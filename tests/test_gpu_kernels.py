@@ -518,7 +518,8 @@ def test_grid_search_large_cloud_vs_oracle_and_auto_dispatch(dc):
 
 
 def test_batched_grid_search_bit_identical_to_brute_force(dc):
-    """dc_knn_grid_batched (one grid per graph of a batch) == dc_knn (tiled brute force) bit for bit, incl. neighbour order:
+    """dc_knn_grid_batched / dc_radius_grid_batched (one grid per graph of a batch) == dc_knn / dc_radius (tiled brute force) bit for
+    bit, incl. neighbour order and the radius search's truncation to the lowest indices:
     a ragged batch of uniform / clustered / degenerate clouds with an empty graph, a one-point graph and a graph with fewer
     than k points in between; several k, loop on / off; through ``ptr`` and through a ``batch`` vector; auto dispatch by the
     average cloud size; the device-side hand-back of a batch a grid cannot split."""
@@ -548,6 +549,14 @@ def test_batched_grid_search_bit_identical_to_brute_force(dc):
                 if want_grid is not None:
                     assert ops.grid_took_it(out) == want_grid
                 assert torch.equal(ops.knn_table(pos, k, batch=batch, loop=loop), ref)
+            for r, mx, loop in ((0.05, 32, False), (0.2, 5, False), (0.1, 64, True), (0.0, 8, False), (1.0e-3, 16, False)):
+                ops.KNN_MODE = "brute"
+                ref, rc = ops.radius_table(pos, r, ptr=ptr, loop=loop, max_num_neighbors=mx)
+                ops.KNN_MODE = "grid"
+                out_r, oc = ops.radius_table(pos, r, ptr=ptr, loop=loop, max_num_neighbors=mx)
+                assert torch.equal(out_r, ref) and torch.equal(oc, rc), f"batched radius r={r} max={mx} loop={loop}"
+                if want_grid is not None:
+                    assert ops.grid_took_it(out_r) == want_grid
         # neighbours never cross graph boundaries
         gid = batch[out.clamp(min=0).long()]
         assert bool(((gid == batch[:, None]) | (out < 0)).all())
