@@ -325,3 +325,26 @@ def test_product_modules_have_no_undefined_names():
                     and n not in ("__file__", "__name__", "__doc__"):
                 bad.append((os.path.basename(f), "<module>", n))
     assert not bad, bad
+
+
+def test_batched_grid_cell_ranges_do_not_overlap():
+    """K4g batched (csrc/knn_grid.cu): graph b owns the cells [base_b, base_b + cells_b) of one cell array with
+    base_b = 2 * (ptr[b] // 8) + 66 * b in closed form (no prefix sum on the device).  A graph of n points uses at most
+    2 * max(n // 8, 1) + 64 cells (grid_max_cells): the ranges must not overlap and must fit batched_total_cells — restated here
+    because an overflow would be silent out-of-bounds counting."""
+    import random
+    rnd = random.Random(0)
+    target = lambda n: max(n // 8, 1)
+    max_cells = lambda n: 2 * target(n) + 64
+    base = lambda first, b: 2 * (first // 8) + 66 * b
+    total = lambda N, B: 2 * (N // 8) + 66 * B + 2
+    for trial in range(2000):
+        B = rnd.choice([2, 3, 7, 64, 500])
+        sizes = [rnd.choice([0, 0, 1, 5, 7, 8, 9, 63, 64, 250, 2000, 5000, rnd.randrange(0, 40000)]) for _ in range(B)]
+        ptr = [0]
+        for n in sizes:
+            ptr.append(ptr[-1] + n)
+        for b in range(B):
+            end = base(ptr[b], b) + max_cells(sizes[b])
+            nxt = base(ptr[b + 1], b + 1) if b + 1 < B else total(ptr[-1], B)
+            assert end <= nxt, (sizes, b)
