@@ -17,6 +17,7 @@ ops.KNN_MODE = "grid"   # K4g: uniform-grid search (bounding box, counting sort,
 dc.knn_graph(pos, 16); dc.knn_graph(pos, 70, loop=True); dc.radius_graph(pos, 0.2); dc.radius_graph(pos, 0.3, max_num_neighbors=5)
 dc.knn_graph(torch.full((50, 3), 0.5, device="cuda"), 4)
 dc.knn_graph(pos, 8, ptr=ptr3); dc.knn_graph(pos, 40, loop=True, ptr=ptr3)   # one grid per graph (dc_knn_grid_batched), empty graph in between
+dc.radius_graph(pos, 0.3, ptr=ptr3, max_num_neighbors=5); dc.radius_graph(pos, 0.2, ptr=ptr3, loop=True)   # dc_radius_grid_batched
 ops.KNN_MODE = "auto"
 # relabelled large single graph (ops.REORDER): cell order from the grid search, permuted hops, TAGConv fwd + bwd
 big = torch.rand(ops.REORDER_MIN_NODES + 100, 3, device="cuda")
