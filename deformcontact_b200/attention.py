@@ -39,6 +39,30 @@ def _groups(ptr_s, ptr_r, group):
     return [(ptr_s[a], ptr_s[min(a + G, B)], ptr_r[a], ptr_r[min(a + G, B)]) for a in range(0, B, G)]
 
 
+class _Blocks(list):
+    """The per-group [ns_g, nr_g] matrices of one head; ``whole`` = the [sum ns_g, nr] matrix they are row blocks of when every
+    group has the same number of collider nodes (the regular case: equal collider meshes, ``attn_group`` graphs per group)."""
+    whole = None
+
+
+def _group_matrices(live, dev):
+    """Uninitialised score / weight matrices of the live groups, rows 16-byte aligned (TMA operands of the batched products)."""
+    widths = {r1 - r0 for _, _, r0, r1 in live}
+    out = _Blocks()
+    if len(widths) == 1:
+        nr = widths.pop()
+        ld = (nr + 3) // 4 * 4
+        whole = torch.empty((sum(s1 - s0 for s0, s1, _, _ in live), ld), dtype=_f32, device=dev)[:, :nr]
+        row = 0
+        for s0, s1, _, _ in live:
+            out.append(whole[row:row + s1 - s0])
+            row += s1 - s0
+        out.whole = whole
+    else:
+        out.extend(torch.empty((s1 - s0, (r1 - r0 + 3) // 4 * 4), dtype=_f32, device=dev)[:, :r1 - r0] for s0, s1, r0, r1 in live)
+    return out
+
+
 class _AttnFn(torch.autograd.Function):
     """All heads at once: every product type is ONE batched launch over heads x groups."""
 
@@ -64,13 +88,16 @@ class _AttnFn(torch.autograd.Function):
             W, b = params[2 * h], params[2 * h + 1]
             qs.append(ops.gemm([(xs, W)], Ns, F, trans_b=True, bias=b))     # L_h(x_resting)  [Ns, F]
             ks.append(ops.gemm([(xr, W)], Nr, F, trans_b=True, bias=b))     # L_h(x_rigid)    [Nr, F]
-            probs.append([torch.empty((s1 - s0, (r1 - r0 + 3) // 4 * 4), dtype=_f32, device=dev)[:, :r1 - r0]   # 16-byte aligned rows
-                          for s0, s1, r0, r1 in live])
+            probs.append(_group_matrices(live, dev))
         HG = [(h, i, g) for h in range(H) for i, g in enumerate(live)]
         ops.gemm_batched([(qs[h][s0:s1], ks[h][r0:r1], probs[h][i]) for h, i, (s0, s1, r0, r1) in HG], trans_b=True)      # scores
         for h in range(H):
-            for P in probs[h]:
-                softmax_rows_(P)
+            whole = getattr(probs[h], "whole", None)
+            if whole is not None:     # groups of equal width are row blocks of one matrix: one softmax launch per head
+                softmax_rows_(whole)
+            else:
+                for P in probs[h]:
+                    softmax_rows_(P)
         ops.gemm_batched([(probs[h][i], xr[r0:r1], outs[h][s0:s1]) for h, i, (s0, s1, r0, r1) in HG], trans_b=False)      # attn @ x_rigid
         ctx.save_for_backward(xs, xr, *params, *qs, *ks, *outs)
         ctx.probs, ctx.groups, ctx.H = probs, live, H
@@ -96,7 +123,7 @@ class _AttnFn(torch.autograd.Function):
         dq = [new_s((Ns, F), dtype=_f32, device=dev) for _ in range(H)]
         dk = [new_r((Nr, F), dtype=_f32, device=dev) for _ in range(H)]
         dxr_h = [new_r((Nr, F), dtype=_f32, device=dev) for _ in range(H)]
-        dPs = [[torch.empty((P.shape[0], P.stride(0)), dtype=_f32, device=dev)[:, :P.shape[1]] for P in probs[h]] for h in range(H)]
+        dPs = [_group_matrices(live, dev) for _ in range(H)]
         HG = [(h, i, g) for h in range(H) for i, g in enumerate(live)]
         # softmax backward dS = P o (dP - rowsum(dP o P)) fused into the epilogue of dP = dO Xr^T: the row sums equal
         # rowdot(dO, O) because O = P Xr, so they are known before the product starts
