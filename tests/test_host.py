@@ -348,3 +348,18 @@ def test_batched_grid_cell_ranges_do_not_overlap():
             end = base(ptr[b], b) + max_cells(sizes[b])
             nxt = base(ptr[b + 1], b + 1) if b + 1 < B else total(ptr[-1], B)
             assert end <= nxt, (sizes, b)
+
+
+def test_attention_group_matrices_are_row_blocks_of_one_matrix():
+    """attention._group_matrices: groups of equal collider width share ONE [sum ns_g, nr] buffer (one softmax launch per head,
+    rows 16-byte aligned for the TMA operands of the batched products); ragged widths fall back to one buffer per group."""
+    from deformcontact_b200 import attention
+    live = [(0, 300, 0, 762), (300, 500, 762, 1524), (500, 1100, 1524, 2286)]
+    m = attention._group_matrices(live, "cpu")
+    assert m.whole is not None and tuple(m.whole.shape) == (1100, 762) and m.whole.stride(0) == 764
+    assert [tuple(b.shape) for b in m] == [(300, 762), (200, 762), (600, 762)]
+    assert all(b.data_ptr() % 16 == 0 and b.stride(0) % 4 == 0 for b in m)
+    assert m[1].data_ptr() == m.whole[300:].data_ptr() and m[2].data_ptr() == m.whole[500:].data_ptr()
+    ragged = attention._group_matrices([(0, 10, 0, 5), (10, 30, 5, 12)], "cpu")
+    assert ragged.whole is None and [tuple(b.shape) for b in ragged] == [(10, 5), (20, 7)]
+    assert all(b.stride(0) % 4 == 0 for b in ragged)
