@@ -1038,7 +1038,10 @@ int gemm_tc2_batched(const dc_gemm_problem* probs, int count, int transA, int tr
     if (cdiv(q.K, T2_BK) > kb_all) kb_all = cdiv(q.K, T2_BK);
     if (!t2_tepi_operand_ok(q.C, q.ldc) || (q.E && !t2_tepi_operand_ok(q.E, q.lde))) tepi_operands = false;
   }
-  const int tepi = t2_tepi_ok(pair, kb_all, 1, accumulate) && tepi_operands;
+  // mode 3 (lab): batched launches take the TMA epilogue only when a problem carries a fused epilogue operand
+  bool any_e = false;
+  for (int i = 0; i < count; ++i) any_e = any_e || probs[i].E != nullptr;
+  const int tepi = t2_tepi_ok(pair, kb_all, 1, accumulate) && tepi_operands && (t2_tepi_mode() != 3 || any_e);
   for (int i = 0; i < count; ++i) {
     const dc_gemm_problem& q = probs[i];
     DC_REQUIRE(q.M >= 0 && q.N >= 0 && q.K >= 0, DC_EINVAL, "gemm_batched: negative size in problem %d", i);
