@@ -862,13 +862,15 @@ int t2_pair() {
   return pair;
 }
 
-// TMA epilogue (CTA pairs only): DCB200_T2_TEPI = 0 off, 1 (default) for short contractions (K <= 512: the products whose tile
-// time is set by the epilogue — attention scores, the fused softmax-backward product, the K = 256 layer products), 2 for every K
+// TMA epilogue (CTA pairs only): DCB200_T2_TEPI = 0 off, 1 for short contractions (K <= 512: the products whose tile time is set by
+// the epilogue — attention scores, the fused softmax-backward product, the K = 256 layer products), 2 for every K, 3 (default) = as 1,
+// but a batched launch takes it only when a problem carries a fused epilogue operand: the plain batched scores product prefers the
+// fourth pipeline stage (same-box A/B, profiles/r02c_tepi_ab.txt: 92.10 -> 91.79 ms per step)
 int t2_tepi_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("DCB200_T2_TEPI");
-    mode = e ? atoi(e) : 1;
+    mode = e ? atoi(e) : 3;
   }
   return mode;
 }
